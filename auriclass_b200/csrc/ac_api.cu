@@ -1,0 +1,965 @@
+// ac_api.cu -- C ABI of libauriclass_cuda.so (include/auriclass_cuda.h) and the
+// host-side orchestration of the kernels: input arena, segment pipeline on a
+// copy stream + a compute stream, threshold speculation / verification.
+//
+// Boundary being replaced: the `mash sketch` / `mash dist` subprocess calls of
+// auriclass/classes.py:92-104, :576-596, :696-713.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/auriclass_cuda.h"
+#include "ac_common.cuh"
+
+using namespace ac;
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(e_ == cudaErrorMemoryAllocation ? AC_E_NOMEM : AC_E_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                      \
+    } while (0)
+
+// ------------------------------------------------------------------ types
+struct Slab {
+    uint8_t *ptr;
+    size_t cap, used;
+};
+
+struct Piece {                 // contiguous raw text of one file, in stream order
+    const uint8_t *ptr;
+    size_t len;                // may shrink at EOF (trailing blank lines are dropped)
+    int file_idx, fmt;
+    bool first_of_file, last_of_file, append_nl;
+    cudaEvent_t ready;         // H2D copy of the piece's latest bytes (nullptr for device feeds)
+};
+
+struct ac_ctx {
+    int dev;
+    cudaStream_t s_copy, s_comp;
+    uint64_t launches;
+    float last_ms[4];
+    bool profile;
+    size_t cand_cap;           // entries in the candidate / sort buffers
+    SelectBufs sb;
+    bool sb_ok;
+    uint8_t *d_Z;
+    TileSum *d_sums;
+    TileIn *d_tin;
+    JobDev *d_jd, *h_jd;
+    std::vector<Slab> slabs;
+    size_t cur_slab;
+    size_t sk_cap;             // entries in sb.sk_hash / sb.sk_cnt
+    ac_job *active;
+    // dist scratch
+    double *d_dist, *d_p, *h_dist, *h_p;
+    unsigned long long *d_common, *d_denom, *h_common, *h_denom;
+    unsigned long long *d_qmeta, *h_qmeta;  // [3][max_q]: pointer, n, length
+    size_t dist_cap, q_cap;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[3];
+    cudaEvent_t ev_job0, ev_job1;
+};
+
+struct ac_job {
+    ac_ctx *ctx;
+    int k, s, m, mode, use64;
+    uint32_t seed;
+    std::vector<Piece> pieces;
+    // file being fed
+    int cur_file;
+    bool file_open;
+    int cur_fmt;               // -1 until the first non-blank byte is seen
+    uint8_t tail[64];
+    size_t tail_len;
+    // pass state
+    bool pass_started;
+    unsigned long long tau0;
+    bool safe;
+    int passes;
+    size_t proc_piece, proc_off;      // first unprocessed byte
+    size_t pending;                   // fed but unprocessed bytes
+    bool first_of_stream;
+    double cand_bound;                // host-side bound on entries in the candidate buffer
+    uint32_t n_table_host;
+    unsigned long long tau_host;
+    size_t bytes_done, next_mark;
+    bool ended_local;
+};
+
+struct ac_sketch {
+    ac_ctx *ctx;
+    unsigned long long *d_hash;
+    uint32_t *d_cnt;
+    uint64_t n;
+    int k, s, hash_bits;
+    uint64_t length;
+};
+
+struct ac_refs {
+    ac_ctx *ctx;
+    unsigned long long *d_hash, *d_off, *d_len;
+    int n_refs, k, s, hash_bits;
+    uint64_t max_n;
+};
+
+static const size_t SLAB_BYTES = 256u << 20;
+static const size_t HOLD_BACK = 64;
+
+// ------------------------------------------------------------------ library
+extern "C" int ac_abi_version(void) { return AC_ABI_VERSION; }
+
+extern "C" const char *ac_last_error(void) { return g_err; }
+
+extern "C" int ac_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int ac_probe(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(AC_E_CUDA, "no CUDA device visible (%s)", e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+    }
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, 0));
+    if (p.major != 10) return fail(AC_E_CUDA, "device 0 is sm_%d%d; libauriclass_cuda.so is built for sm_100a only", p.major, p.minor);
+    return AC_OK;
+}
+
+extern "C" void *ac_alloc_pinned(size_t n) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault) != cudaSuccess) {
+        fail(AC_E_NOMEM, "cudaHostAlloc(%zu) failed: %s", n, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void ac_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+
+static void free_select(ac_ctx *c) {
+    SelectBufs &b = c->sb;
+    cudaFree(b.keys_a); cudaFree(b.keys_b); cudaFree(b.vals_a); cudaFree(b.vals_b);
+    cudaFree(b.tab_hash); cudaFree(b.tab_cnt); cudaFree(b.start_sum); cudaFree(b.hist); cudaFree(b.tile_tmp);
+    cudaFree(b.sk_hash); cudaFree(b.sk_cnt);
+    memset(&b, 0, sizeof(b));
+    c->sb_ok = false;
+}
+
+static int alloc_select(ac_ctx *c, size_t sk_cap) {
+    SelectBufs &b = c->sb;
+    if (c->sb_ok && sk_cap > c->sk_cap) {
+        cudaFree(b.sk_hash); cudaFree(b.sk_cnt);
+        b.sk_hash = nullptr; b.sk_cnt = nullptr; c->sk_cap = 0;
+        CK(cudaMalloc(&b.sk_hash, sk_cap * 8)); CK(cudaMalloc(&b.sk_cnt, sk_cap * 4));
+        c->sk_cap = sk_cap;
+    }
+    if (c->sb_ok) return AC_OK;
+    memset(&b, 0, sizeof(b));
+    const size_t cap = c->cand_cap;
+    b.cap = cap; b.tab_cap = cap;
+    CK(cudaMalloc(&b.keys_a, cap * 8)); CK(cudaMalloc(&b.keys_b, cap * 8));
+    CK(cudaMalloc(&b.vals_a, cap * 4)); CK(cudaMalloc(&b.vals_b, cap * 4));
+    CK(cudaMalloc(&b.tab_hash, (cap + 1) * 8)); CK(cudaMalloc(&b.tab_cnt, (cap + 1) * 4));
+    CK(cudaMalloc(&b.start_sum, (cap + 2) * 4));
+    const size_t rs_tiles = cap / 4096 + 2;
+    CK(cudaMalloc(&b.hist, (256 * rs_tiles + 256) * 4));
+    CK(cudaMalloc(&b.tile_tmp, (2 * (cap / 2048 + 2)) * 4));
+    CK(cudaMalloc(&b.sk_hash, sk_cap * 8)); CK(cudaMalloc(&b.sk_cnt, sk_cap * 4));
+    c->sk_cap = sk_cap;
+    c->sb_ok = true;
+    return AC_OK;
+}
+
+extern "C" int ac_create(int device, ac_ctx **out) {
+    if (!out) return fail(AC_E_PARAM, "ac_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(AC_E_CUDA, "no CUDA device visible: libauriclass_cuda.so has no CPU path"); }
+    if (device < 0 || device >= n) return fail(AC_E_PARAM, "device %d out of range (0..%d)", device, n - 1);
+    CK(cudaSetDevice(device));
+    ac_ctx *c = new ac_ctx();
+    c->dev = device; c->launches = 0; c->profile = false; c->sb_ok = false; c->active = nullptr;
+    c->cur_slab = 0; c->sk_cap = 0;
+    memset(c->last_ms, 0, sizeof(c->last_ms));
+    memset(&c->sb, 0, sizeof(c->sb));
+    c->d_dist = c->d_p = c->h_dist = c->h_p = nullptr;
+    c->d_common = c->d_denom = c->h_common = c->h_denom = nullptr;
+    c->d_qmeta = c->h_qmeta = nullptr; c->dist_cap = c->q_cap = 0;
+    const char *cap_env = getenv("AC_CAND_CAP");
+    c->cand_cap = cap_env ? (size_t)strtoull(cap_env, nullptr, 10) : ((size_t)48 << 20);
+    if (c->cand_cap < (1u << 16)) c->cand_cap = 1u << 16;
+    CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+    CK(cudaMalloc(&c->d_Z, Z_CARRY + SEG_BYTES + K2_TILE + 4096));
+    const size_t max_tiles = SEG_BYTES / K1_TILE + 4;
+    CK(cudaMalloc(&c->d_sums, max_tiles * sizeof(TileSum)));
+    CK(cudaMalloc(&c->d_tin, max_tiles * sizeof(TileIn)));
+    CK(cudaMalloc(&c->d_jd, sizeof(JobDev)));
+    CK(cudaHostAlloc(&c->h_jd, sizeof(JobDev), cudaHostAllocDefault));
+    CK(cudaEventCreate(&c->ev_job0)); CK(cudaEventCreate(&c->ev_job1));
+    *out = c;
+    return AC_OK;
+}
+
+extern "C" void ac_destroy(ac_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->dev);
+    cudaDeviceSynchronize();
+    free_select(c);
+    cudaFree(c->d_Z); cudaFree(c->d_sums); cudaFree(c->d_tin); cudaFree(c->d_jd); cudaFreeHost(c->h_jd);
+    for (auto &s : c->slabs) cudaFree(s.ptr);
+    cudaFree(c->d_dist); cudaFree(c->d_p); cudaFree(c->d_common); cudaFree(c->d_denom); cudaFree(c->d_qmeta);
+    cudaFreeHost(c->h_dist); cudaFreeHost(c->h_p); cudaFreeHost(c->h_common); cudaFreeHost(c->h_denom); cudaFreeHost(c->h_qmeta);
+    for (auto ev : c->ev_pool) cudaEventDestroy(ev);
+    for (int i = 0; i < 3; i++) for (auto &p : c->prof[i]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    cudaEventDestroy(c->ev_job0); cudaEventDestroy(c->ev_job1);
+    cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_comp);
+    delete c;
+}
+
+extern "C" int ac_sync(ac_ctx *c) {
+    if (!c) return fail(AC_E_PARAM, "ac_sync: ctx is NULL");
+    CK(cudaSetDevice(c->dev));
+    CK(cudaStreamSynchronize(c->s_copy));
+    CK(cudaStreamSynchronize(c->s_comp));
+    return AC_OK;
+}
+
+extern "C" uint64_t ac_launch_count(const ac_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int ac_set_profile(ac_ctx *c, int on) {
+    if (!c) return fail(AC_E_PARAM, "ctx is NULL");
+    c->profile = on != 0;
+    return AC_OK;
+}
+
+extern "C" int ac_last_job_times(const ac_ctx *c, float ms[4]) {
+    if (!c || !ms) return fail(AC_E_PARAM, "ac_last_job_times: NULL argument");
+    memcpy(ms, c->last_ms, sizeof(c->last_ms));
+    return AC_OK;
+}
+
+extern "C" int ac_int_peak(ac_ctx *c, double *instr_per_s) {
+    if (!c || !instr_per_s) return fail(AC_E_PARAM, "ac_int_peak: NULL argument");
+    CK(cudaSetDevice(c->dev));
+    LaunchCtx lc{c->s_comp, &c->launches};
+    *instr_per_s = run_int_peak(lc);
+    CK(cudaGetLastError());
+    return AC_OK;
+}
+
+// ------------------------------------------------------------------ profiling helpers
+struct ProfScope {
+    ac_ctx *c; int slot; cudaEvent_t a, b; bool on;
+    ProfScope(ac_ctx *c_, int slot_) : c(c_), slot(slot_), a(nullptr), b(nullptr), on(c_->profile) {
+        if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, c->s_comp); }
+    }
+    ~ProfScope() { if (on) { cudaEventRecord(b, c->s_comp); c->prof[slot].push_back({a, b}); } }
+};
+
+static void prof_collect(ac_ctx *c) {
+    for (int i = 0; i < 3; i++) {
+        float tot = 0;
+        for (auto &p : c->prof[i]) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) tot += ms;
+            cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+        }
+        c->prof[i].clear();
+        c->last_ms[i] = tot;
+    }
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev_job0, c->ev_job1) == cudaSuccess) c->last_ms[3] = ms;
+    cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ sketch job
+static bool is_blank(uint8_t ch) { return ch == '\n' || ch == '\r' || ch == ' ' || ch == '\t'; }
+
+extern "C" int ac_sketch_begin(ac_ctx *c, int k, int sketch_size, uint32_t seed, int min_copies, int mode, ac_job **out) {
+    if (!c || !out) return fail(AC_E_PARAM, "ac_sketch_begin: NULL argument");
+    *out = nullptr;
+    if (k < 1 || k > 32) return fail(AC_E_PARAM, "k = %d outside 1..32", k);
+    if (sketch_size < 1 || sketch_size > (1 << 24)) return fail(AC_E_PARAM, "sketch size %d outside 1..2^24", sketch_size);
+    if (min_copies < 1) return fail(AC_E_PARAM, "min_copies = %d < 1", min_copies);
+    if (mode != AC_MODE_READS && mode != AC_MODE_FASTA) return fail(AC_E_PARAM, "unknown mode %d", mode);
+    if (c->active) return fail(AC_E_STATE, "context already has an active sketch job");
+    CK(cudaSetDevice(c->dev));
+    {
+        int rc = alloc_select(c, (size_t)sketch_size);
+        if (rc) { free_select(c); return rc; }
+    }
+    ac_job *j = new ac_job();
+    j->ctx = c; j->k = k; j->s = sketch_size; j->m = (mode == AC_MODE_FASTA) ? 1 : min_copies; j->mode = mode;
+    j->use64 = k > 16 ? 1 : 0; j->seed = seed;
+    j->cur_file = -1; j->file_open = false; j->cur_fmt = -1; j->tail_len = 0;
+    j->pass_started = false; j->tau0 = 0; j->safe = false; j->passes = 0;
+    j->proc_piece = 0; j->proc_off = 0; j->pending = 0; j->first_of_stream = true;
+    j->cand_bound = 0; j->n_table_host = 0; j->tau_host = 0; j->bytes_done = 0; j->next_mark = 0; j->ended_local = false;
+    for (auto &s : c->slabs) s.used = 0;
+    c->cur_slab = 0;
+    c->active = j;
+    *out = j;
+    return AC_OK;
+}
+
+static void job_free(ac_job *j) {
+    if (!j) return;
+    ac_ctx *c = j->ctx;
+    cudaStreamSynchronize(c->s_copy);
+    cudaStreamSynchronize(c->s_comp);
+    for (auto &p : j->pieces) if (p.ready) c->ev_pool.push_back(p.ready);
+    if (c->active == j) c->active = nullptr;
+    delete j;
+}
+
+extern "C" void ac_sketch_abort(ac_job *j) { if (j) { cudaSetDevice(j->ctx->dev); job_free(j); } }
+
+static unsigned long long space_max(const ac_job *j) { return j->use64 ? ~0ULL : 0xffffffffULL; }
+
+static int read_jd(ac_ctx *c) {
+    CK(cudaMemcpyAsync(c->h_jd, c->d_jd, sizeof(JobDev), cudaMemcpyDeviceToHost, c->s_comp));
+    CK(cudaStreamSynchronize(c->s_comp));
+    return AC_OK;
+}
+
+static int key_bits_for(unsigned long long tau) {
+    int b = 64;
+    while (b > 8 && !(tau >> (b - 1))) b--;
+    return b;
+}
+
+// fold the candidate buffer into the table; one host sync to learn the sizes
+static int consolidate(ac_job *j) {
+    ac_ctx *c = j->ctx;
+    int rc = read_jd(c);
+    if (rc) return rc;
+    const JobDev &h = *c->h_jd;
+    if (h.overflow) return AC_OK;  // the pass is void; the caller re-runs it in safe mode
+    const unsigned long long n_cand = h.cand_count;
+    const uint32_t n_table = h.n_table;
+    if (n_cand + n_table > c->sb.cap) return fail(AC_E_NOMEM, "candidate table needs %llu entries, capacity %zu (raise AC_CAND_CAP)", n_cand + n_table, c->sb.cap);
+    LaunchCtx lc{c->s_comp, &c->launches};
+    {
+        ProfScope ps(c, 2);
+        launch_consolidate(lc, c->sb, c->d_jd, n_cand, n_table, key_bits_for(h.tau), j->s, j->m);
+    }
+    CK(cudaGetLastError());
+    j->cand_bound = 0;
+    j->tau_host = h.tau;              // stale (pre-consolidation) value: an upper bound of the new tau
+    j->n_table_host = (uint32_t)std::min<unsigned long long>(n_cand + n_table, 0xffffffffULL);  // upper bound
+    return AC_OK;
+}
+
+static int start_pass(ac_job *j, unsigned long long tau0, bool safe) {
+    ac_ctx *c = j->ctx;
+    JobDev z;
+    memset(&z, 0, sizeof(z));
+    z.at_line_start = 1;
+    z.tau = tau0;
+    z.n_zbuf = Z_CARRY;
+    *c->h_jd = z;
+    CK(cudaMemcpyAsync(c->d_jd, c->h_jd, sizeof(JobDev), cudaMemcpyHostToDevice, c->s_comp));
+    CK(cudaStreamSynchronize(c->s_comp));
+    j->pass_started = true; j->tau0 = tau0; j->safe = safe; j->passes++;
+    j->proc_piece = 0; j->proc_off = 0; j->first_of_stream = true;
+    j->cand_bound = 0; j->n_table_host = 0; j->tau_host = tau0; j->bytes_done = 0; j->next_mark = 2 * SEG_BYTES;
+    if (j->passes == 1) CK(cudaEventRecord(c->ev_job0, c->s_comp));
+    return AC_OK;
+}
+
+// run K1 + K2 over bytes [off, off+len) of piece pi (len <= SEG_BYTES)
+static int run_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_of_file) {
+    ac_ctx *c = j->ctx;
+    const Piece &p = j->pieces[pi];
+    LaunchCtx lc{c->s_comp, &c->launches};
+    const bool append_nl = last_of_file && p.append_nl;
+    const size_t seg_len = len + (append_nl ? 1 : 0);
+    // candidate-buffer headroom: consolidate first when this segment could overflow it
+    const double frac = j->safe ? 1.0 : std::min(1.0, ((double)j->tau_host + 1.0) / ((double)space_max(j) + 1.0) * 2.0 + 1e-3);
+    const double seg_bound = j->safe ? (double)seg_len : (double)seg_len * frac + 65536.0;
+    if (j->cand_bound > 0 && j->cand_bound + seg_bound + j->n_table_host > (double)c->sb.cap) {
+        int rc = consolidate(j);
+        if (rc) return rc;
+    }
+    if (p.ready) CK(cudaStreamWaitEvent(c->s_comp, p.ready, 0));
+    SegDesc sd;
+    const uintptr_t addr = (uintptr_t)(p.ptr + off);
+    sd.base = (const uint8_t *)(addr & ~(uintptr_t)15);
+    sd.skip = (uint32_t)(addr & 15);
+    sd.len = (uint32_t)seg_len;
+    sd.n_tiles = seg_len ? div_up(sd.skip + seg_len, K1_TILE) : 0;
+    sd.append_nl = append_nl ? 1 : 0;
+    sd.fmt = p.fmt;
+    sd.first_of_stream = j->first_of_stream ? 1 : 0;
+    sd.last_of_file = last_of_file ? 1 : 0;
+    {
+        ProfScope ps(c, 0);
+        launch_parse_segment(lc, sd, c->d_sums, c->d_tin, c->d_jd, c->d_Z);
+    }
+    {
+        ProfScope ps(c, 1);
+        launch_hash_segment(lc, j->k, c->d_Z, (uint32_t)(Z_CARRY + seg_len + 1), c->d_jd, c->sb.keys_a, c->sb.cap, j->seed, j->use64);
+    }
+    CK(cudaGetLastError());
+    j->first_of_stream = false;
+    j->cand_bound += seg_bound;
+    j->bytes_done += seg_len;
+    if (j->safe || j->bytes_done >= j->next_mark) {
+        int rc = consolidate(j);
+        if (rc) return rc;
+        while (j->next_mark <= j->bytes_done) j->next_mark *= 2;
+    }
+    return AC_OK;
+}
+
+// process fed bytes; `all` = flush everything (job end), else only full segments once enough has
+// been fed, keeping HOLD_BACK bytes of a still-open file (EOF may trim trailing blank lines)
+static int pump(ac_job *j, bool all) {
+    while (j->proc_piece < j->pieces.size()) {
+        const Piece &p = j->pieces[j->proc_piece];
+        const bool is_last_piece = j->proc_piece + 1 == j->pieces.size();
+        const bool open = is_last_piece && !p.last_of_file;
+        const size_t avail = p.len - j->proc_off;
+        const size_t usable = open ? (avail > HOLD_BACK ? avail - HOLD_BACK : 0) : avail;
+        if (open && usable == 0) break;
+        const size_t len = std::min(usable, SEG_BYTES);
+        const bool seg_last = p.last_of_file && (j->proc_off + len == p.len);
+        if (!all) {
+            if (j->pending < SEG_BYTES + HOLD_BACK) break;
+            if (open && len < SEG_BYTES) break;
+        }
+        if (!j->pass_started) {
+            // the size fed so far decides the speculative threshold: big inputs start at 1/16 of
+            // the hash space, small ones keep everything (tau = max, nothing to verify)
+            const bool big = j->pending >= SEG_BYTES;
+            int rc = start_pass(j, big ? (space_max(j) >> 4) : space_max(j), !big);
+            if (rc) return rc;
+        }
+        int rc = run_segment(j, j->proc_piece, j->proc_off, len, seg_last);
+        if (rc) return rc;
+        j->pending -= std::min(j->pending, len);
+        j->proc_off += len;
+        if (j->proc_off == p.len && !open) { j->proc_piece++; j->proc_off = 0; }
+    }
+    return AC_OK;
+}
+
+// close the file being fed: trailing blank lines are dropped, a missing final newline is added virtually
+static void close_file(ac_job *j) {
+    if (!j->file_open) return;
+    j->file_open = false;
+    // last piece of this file
+    Piece *last = nullptr;
+    for (auto it = j->pieces.rbegin(); it != j->pieces.rend(); ++it)
+        if (it->file_idx == j->cur_file) { last = &*it; break; }
+    if (!last) return;
+    last->last_of_file = true;
+    size_t t = j->tail_len, blank = 0;
+    while (blank < t && is_blank(j->tail[t - 1 - blank])) blank++;
+    // inside the trailing blank run keep everything up to its first '\n'
+    size_t first_nl = (size_t)-1;
+    for (size_t i = t - blank; i < t; i++) if (j->tail[i] == '\n') { first_nl = i; break; }
+    if (first_nl == (size_t)-1) last->append_nl = true;
+    else {
+        size_t drop = t - 1 - first_nl;
+        drop = std::min(drop, last->len);
+        last->len -= drop;
+        j->pending -= std::min(j->pending, drop);
+        last->append_nl = false;
+    }
+}
+
+static void push_tail(ac_job *j, const uint8_t *p, size_t n) {
+    if (n >= sizeof(j->tail)) { memcpy(j->tail, p + n - sizeof(j->tail), sizeof(j->tail)); j->tail_len = sizeof(j->tail); return; }
+    const size_t keep = std::min(j->tail_len, sizeof(j->tail) - n);
+    memmove(j->tail, j->tail + j->tail_len - keep, keep);
+    memcpy(j->tail + keep, p, n);
+    j->tail_len = keep + n;
+}
+
+static int feed_common(ac_job *j, const uint8_t *src, size_t n, int file_idx, int eof, bool on_device) {
+    if (!j) return fail(AC_E_PARAM, "ac_sketch_feed: job is NULL");
+    ac_ctx *c = j->ctx;
+    if (j->ended_local) return fail(AC_E_STATE, "feed after end");
+    if (n && !src) return fail(AC_E_PARAM, "ac_sketch_feed: NULL buffer with n = %zu", n);
+    CK(cudaSetDevice(c->dev));
+    if (!j->file_open || file_idx != j->cur_file) {
+        if (j->file_open) close_file(j);
+        if (j->mode == AC_MODE_FASTA && !j->pieces.empty())
+            return fail(AC_E_STATE, "AC_MODE_FASTA sketches one file per job (mash sketch without -r)");
+        j->cur_file = file_idx; j->file_open = true; j->cur_fmt = -1; j->tail_len = 0;
+    }
+    // host view of the head (format sniffing) and tail (EOF trimming) of the chunk
+    uint8_t headbuf[64], tailbuf[64];
+    const uint8_t *hsrc = src;
+    size_t skip = 0;
+    if (n) {
+        if (j->cur_fmt < 0) {
+            // skip leading blanks, sniff '>' / '@'
+            if (on_device) {
+                size_t pos = 0;
+                while (pos < n && j->cur_fmt < 0) {
+                    const size_t m = std::min(sizeof(headbuf), n - pos);
+                    CK(cudaMemcpy(headbuf, src + pos, m, cudaMemcpyDeviceToHost));
+                    size_t i = 0;
+                    while (i < m && is_blank(headbuf[i])) i++;
+                    pos += i;
+                    if (i < m) { j->cur_fmt = headbuf[i] == '>' ? FMT_FASTA : (headbuf[i] == '@' ? FMT_FASTQ : -2); break; }
+                }
+                skip = pos;
+            } else {
+                while (skip < n && is_blank(hsrc[skip])) skip++;
+                if (skip < n) j->cur_fmt = hsrc[skip] == '>' ? FMT_FASTA : (hsrc[skip] == '@' ? FMT_FASTQ : -2);
+            }
+        }
+        if (j->cur_fmt == -2) {
+            // neither FASTA nor FASTQ: kseq finds no record start in such a file;
+            // we do not scan it for a later '>' / '@' -- report it
+            return fail(AC_E_FORMAT, "file %d starts with neither '>' nor '@'", file_idx);
+        }
+        const size_t m = n - skip;
+        if (m && j->cur_fmt >= 0) {
+            if (on_device) {
+                const size_t tl = std::min(sizeof(tailbuf), m);
+                CK(cudaMemcpy(tailbuf, src + n - tl, tl, cudaMemcpyDeviceToHost));
+                push_tail(j, tailbuf, tl);
+                Piece p;
+                p.ptr = src + skip; p.len = m; p.file_idx = file_idx; p.fmt = j->cur_fmt;
+                p.first_of_file = true; p.last_of_file = false; p.append_nl = false; p.ready = nullptr;
+                for (auto &q : j->pieces) if (q.file_idx == file_idx) p.first_of_file = false;
+                j->pieces.push_back(p);
+            } else {
+                push_tail(j, hsrc + skip, m);
+                // place the bytes in the arena
+                Slab *sl = nullptr;
+                if (c->cur_slab < c->slabs.size() && c->slabs[c->cur_slab].cap - c->slabs[c->cur_slab].used >= m + 64)
+                    sl = &c->slabs[c->cur_slab];
+                else {
+                    // never reuse a slab that holds earlier bytes of this job: they are retained for re-runs
+                    for (size_t i = c->cur_slab + (c->slabs.empty() ? 0 : 1); i < c->slabs.size(); i++)
+                        if (c->slabs[i].used == 0 && c->slabs[i].cap >= m + 64) { sl = &c->slabs[i]; c->cur_slab = i; break; }
+                    if (!sl && c->cur_slab < c->slabs.size() && c->slabs[c->cur_slab].used == 0 &&
+                        c->slabs[c->cur_slab].cap >= m + 64)
+                        sl = &c->slabs[c->cur_slab];
+                }
+                if (!sl) {
+                    Slab ns;
+                    ns.cap = std::max(SLAB_BYTES, m + 4096); ns.used = 0; ns.ptr = nullptr;
+                    CK(cudaMalloc(&ns.ptr, ns.cap));
+                    c->slabs.push_back(ns);
+                    c->cur_slab = c->slabs.size() - 1;
+                    sl = &c->slabs.back();
+                }
+                uint8_t *dst = sl->ptr + sl->used;
+                CK(cudaMemcpyAsync(dst, hsrc + skip, m, cudaMemcpyHostToDevice, c->s_copy));
+                sl->used += m;
+                cudaEvent_t ev;
+                if (!c->ev_pool.empty()) { ev = c->ev_pool.back(); c->ev_pool.pop_back(); }
+                else CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                CK(cudaEventRecord(ev, c->s_copy));
+                Piece *prev = j->pieces.empty() ? nullptr : &j->pieces.back();
+                if (prev && prev->file_idx == file_idx && !prev->last_of_file && prev->ptr + prev->len == dst &&
+                    j->proc_piece < j->pieces.size()) {
+                    prev->len += m;
+                    if (prev->ready) c->ev_pool.push_back(prev->ready);
+                    prev->ready = ev;
+                } else {
+                    Piece p;
+                    p.ptr = dst; p.len = m; p.file_idx = file_idx; p.fmt = j->cur_fmt;
+                    p.first_of_file = true; p.last_of_file = false; p.append_nl = false; p.ready = ev;
+                    for (auto &q : j->pieces) if (q.file_idx == file_idx) p.first_of_file = false;
+                    j->pieces.push_back(p);
+                }
+            }
+            j->pending += m;
+        }
+    }
+    if (eof) close_file(j);
+    return pump(j, false);
+}
+
+extern "C" int ac_sketch_feed(ac_job *j, const uint8_t *host, size_t n, int file_idx, int eof) {
+    return feed_common(j, host, n, file_idx, eof, false);
+}
+extern "C" int ac_sketch_feed_device(ac_job *j, const uint8_t *dev, size_t n, int file_idx, int eof) {
+    return feed_common(j, dev, n, file_idx, eof, true);
+}
+extern "C" int ac_sketch_feed_wait(ac_job *j) {
+    if (!j) return fail(AC_E_PARAM, "job is NULL");
+    CK(cudaSetDevice(j->ctx->dev));
+    CK(cudaStreamSynchronize(j->ctx->s_copy));
+    return AC_OK;
+}
+
+static void fill_info(const ac_job *j, const JobDev &h, ac_sketch_info *info) {
+    if (!info) return;
+    memset(info, 0, sizeof(*info));
+    info->n_hashes = h.n_sketch;
+    info->n_records = h.n_records;
+    info->n_kept = h.n_kept;
+    info->total_len = h.n_bases - h.n_short_len;
+    info->n_kmers = h.n_kmers;
+    info->n_candidates = h.cand_total;
+    info->max_hash = h.max_hash;
+    info->sum_counts = h.sum_counts;
+    info->final_tau = h.tau;
+    info->genome_size = h.genome_size;
+    info->coverage = h.coverage;
+    info->hash_bits = j->use64 ? 64 : 32;
+    info->passes = j->passes;
+}
+
+// finish the local pass (all ranks): returns with the final table on the device and h_jd current
+static int finish_local(ac_job *j) {
+    ac_ctx *c = j->ctx;
+    if (j->file_open) close_file(j);
+    for (int attempt = 0; attempt < 4; attempt++) {
+        int rc = pump(j, true);
+        if (rc) return rc;
+        if (!j->pass_started) {  // nothing was fed at all
+            rc = start_pass(j, space_max(j), true);
+            if (rc) return rc;
+        }
+        rc = consolidate(j);
+        if (rc) return rc;
+        rc = read_jd(c);
+        if (rc) return rc;
+        const JobDev &h = *c->h_jd;
+        if (h.format_error) {
+            const char *what = (h.format_error & FERR_FQ_HEADER) ? "a FASTQ record does not start with '@' (multi-line FASTQ is not supported)"
+                             : (h.format_error & FERR_FQ_PLUS) ? "third line of a FASTQ record does not start with '+' (multi-line FASTQ is not supported)"
+                             : (h.format_error & FERR_FQ_TRUNC) ? "FASTQ input is truncated or sequence/quality lengths differ"
+                             : "'+' line inside FASTA input";
+            return fail(AC_E_FORMAT, "input rejected by the GPU parser: %s", what);
+        }
+        const bool spec_failed = !h.overflow && j->tau0 != space_max(j) && h.n_qualified < (uint32_t)j->s;
+        if (!h.overflow && !spec_failed) return AC_OK;
+        if (h.overflow && j->safe) return fail(AC_E_NOMEM, "candidate buffer overflow in safe mode (raise AC_CAND_CAP, now %zu)", c->sb.cap);
+        // repeat the pass over the retained input: same threshold in safe mode after an overflow,
+        // full hash space after a failed speculation
+        rc = start_pass(j, spec_failed ? space_max(j) : j->tau0, true);
+        if (rc) return rc;
+        j->pending = 0;
+        for (auto &p : j->pieces) j->pending += p.len;
+    }
+    return fail(AC_E_INTERNAL, "threshold search did not converge");
+}
+
+static int make_sketch(ac_ctx *c, const unsigned long long *d_hash, const uint32_t *d_cnt, uint64_t n, int k, int s,
+                       int hash_bits, uint64_t length, ac_sketch **out) {
+    ac_sketch *sk = new ac_sketch();
+    sk->ctx = c; sk->n = n; sk->k = k; sk->s = s; sk->hash_bits = hash_bits; sk->length = length;
+    sk->d_hash = nullptr; sk->d_cnt = nullptr;
+    cudaError_t e = cudaMalloc(&sk->d_hash, (n ? n : 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&sk->d_cnt, (n ? n : 1) * 4);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(sk->d_hash, d_hash, n * 8, cudaMemcpyDeviceToDevice, c->s_comp);
+    if (e == cudaSuccess && n) {
+        if (d_cnt) e = cudaMemcpyAsync(sk->d_cnt, d_cnt, n * 4, cudaMemcpyDeviceToDevice, c->s_comp);
+        else e = cudaMemsetAsync(sk->d_cnt, 0, n * 4, c->s_comp);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_comp);
+    if (e != cudaSuccess) {
+        cudaFree(sk->d_hash); cudaFree(sk->d_cnt); delete sk;
+        return fail(AC_E_CUDA, "sketch allocation/copy failed: %s", cudaGetErrorString(e));
+    }
+    *out = sk;
+    return AC_OK;
+}
+
+extern "C" int ac_sketch_end(ac_job *j, ac_sketch **out, ac_sketch_info *info) {
+    if (!j || !out) { if (j) job_free(j); return fail(AC_E_PARAM, "ac_sketch_end: NULL argument"); }
+    *out = nullptr;
+    ac_ctx *c = j->ctx;
+    cudaSetDevice(c->dev);
+    int rc = finish_local(j);
+    if (rc) { job_free(j); return rc; }
+    LaunchCtx lc{c->s_comp, &c->launches};
+    {
+        ProfScope ps(c, 2);
+        launch_finalize(lc, c->sb, c->d_jd, j->use64);
+    }
+    cudaEventRecord(c->ev_job1, c->s_comp);
+    rc = read_jd(c);
+    if (rc) { job_free(j); return rc; }
+    prof_collect(c);
+    const JobDev h = *c->h_jd;
+    fill_info(j, h, info);
+    if (h.n_sketch == 0) {
+        job_free(j);
+        // Mash: "ERROR: Did not find fasta records in ..." (no record >= k, or no hash reached -m)
+        return fail(AC_E_NO_RECORDS, "did not find sequence records (records: %llu, of length >= k: %llu, k-mers: %llu)",
+                    h.n_records, h.n_kept, h.n_kmers);
+    }
+    const uint64_t length = (j->mode == AC_MODE_FASTA) ? (h.n_bases - h.n_short_len) : (uint64_t)h.genome_size;
+    rc = make_sketch(c, c->sb.sk_hash, c->sb.sk_cnt, h.n_sketch, j->k, j->s, j->use64 ? 64 : 32, length, out);
+    job_free(j);
+    return rc;
+}
+
+// ------------------------------------------------------------------ multi-GPU pieces
+extern "C" int ac_sketch_end_local(ac_job *j, uint64_t *n_entries, uint64_t *tau, int *speculative, ac_sketch_info *info) {
+    if (!j) return fail(AC_E_PARAM, "job is NULL");
+    ac_ctx *c = j->ctx;
+    CK(cudaSetDevice(c->dev));
+    int rc = finish_local(j);
+    if (rc) return rc;
+    const JobDev &h = *c->h_jd;
+    j->ended_local = true;
+    if (n_entries) *n_entries = h.n_table;
+    if (tau) *tau = h.tau;
+    if (speculative) *speculative = 0;  // finish_local already repeated a failed speculation locally
+    fill_info(j, h, info);
+    return AC_OK;
+}
+
+extern "C" int ac_job_table_ranges(ac_job *j, uint64_t tau_cut, int n_ranges, uint64_t *range_begin) {
+    if (!j || !range_begin || n_ranges < 1) return fail(AC_E_PARAM, "ac_job_table_ranges: bad argument");
+    if (!j->ended_local) return fail(AC_E_STATE, "call ac_sketch_end_local first");
+    ac_ctx *c = j->ctx;
+    CK(cudaSetDevice(c->dev));
+    const uint32_t n = c->h_jd->n_table;
+    std::vector<unsigned long long> h(n);
+    if (n) CK(cudaMemcpy(h.data(), c->sb.tab_hash, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    // owner of hash x = floor(x * P / (tau_cut + 1)); boundaries b_r = ceil(r * (tau_cut + 1) / P)
+    const unsigned __int128 span = (unsigned __int128)tau_cut + 1;
+    for (int r = 0; r <= n_ranges; r++) {
+        if (r == n_ranges) {
+            range_begin[r] = std::upper_bound(h.begin(), h.end(), (unsigned long long)tau_cut) - h.begin();
+        } else {
+            const unsigned __int128 b = (span * (unsigned)r + (unsigned)n_ranges - 1) / (unsigned)n_ranges;
+            range_begin[r] = std::lower_bound(h.begin(), h.end(), (unsigned long long)b) - h.begin();
+        }
+    }
+    return AC_OK;
+}
+
+extern "C" int ac_job_table_export(ac_job *j, uint64_t begin, uint64_t end, uint64_t *dev_hashes, uint32_t *dev_counts) {
+    if (!j) return fail(AC_E_PARAM, "job is NULL");
+    if (!j->ended_local) return fail(AC_E_STATE, "call ac_sketch_end_local first");
+    ac_ctx *c = j->ctx;
+    CK(cudaSetDevice(c->dev));
+    if (end < begin || end > c->h_jd->n_table) return fail(AC_E_PARAM, "table range [%llu,%llu) outside 0..%u",
+                                                            (unsigned long long)begin, (unsigned long long)end, c->h_jd->n_table);
+    const size_t n = end - begin;
+    if (n) {
+        CK(cudaMemcpyAsync(dev_hashes, c->sb.tab_hash + begin, n * 8, cudaMemcpyDeviceToDevice, c->s_comp));
+        CK(cudaMemcpyAsync(dev_counts, c->sb.tab_cnt + begin, n * 4, cudaMemcpyDeviceToDevice, c->s_comp));
+    }
+    CK(cudaStreamSynchronize(c->s_comp));
+    return AC_OK;
+}
+
+extern "C" int ac_merge_counts(ac_ctx *c, uint64_t *dev_hashes, uint32_t *dev_counts, uint64_t n, int min_copies, uint64_t *n_out) {
+    if (!c || !n_out) return fail(AC_E_PARAM, "ac_merge_counts: NULL argument");
+    CK(cudaSetDevice(c->dev));
+    *n_out = 0;
+    if (n == 0) return AC_OK;
+    int rc = alloc_select(c, 1024);
+    if (rc) return rc;
+    if (n > c->sb.cap) return fail(AC_E_NOMEM, "merge of %llu entries exceeds capacity %zu", (unsigned long long)n, c->sb.cap);
+    CK(cudaMemcpyAsync(c->sb.keys_a, dev_hashes, n * 8, cudaMemcpyDeviceToDevice, c->s_comp));
+    CK(cudaMemcpyAsync(c->sb.vals_a, dev_counts, n * 4, cudaMemcpyDeviceToDevice, c->s_comp));
+    LaunchCtx lc{c->s_comp, &c->launches};
+    launch_merge_counts(lc, c->sb, c->d_jd, n, min_copies);
+    CK(cudaGetLastError());
+    rc = read_jd(c);
+    if (rc) return rc;
+    const uint64_t nq = c->h_jd->n_qualified;
+    if (nq) {
+        CK(cudaMemcpyAsync(dev_hashes, c->sb.keys_a, nq * 8, cudaMemcpyDeviceToDevice, c->s_comp));
+        CK(cudaMemcpyAsync(dev_counts, c->sb.vals_a, nq * 4, cudaMemcpyDeviceToDevice, c->s_comp));
+        CK(cudaStreamSynchronize(c->s_comp));
+    }
+    *n_out = nq;
+    return AC_OK;
+}
+
+__global__ void k_set_nsketch(JobDev *jd, uint32_t n) { jd->n_sketch = n; }
+
+extern "C" int ac_sketch_from_table(ac_ctx *c, const uint64_t *dev_hashes, const uint32_t *dev_counts, uint64_t n, int k,
+                                    int sketch_size, ac_sketch **out, ac_sketch_info *info) {
+    if (!c || !out) return fail(AC_E_PARAM, "ac_sketch_from_table: NULL argument");
+    *out = nullptr;
+    CK(cudaSetDevice(c->dev));
+    const uint64_t ns = std::min<uint64_t>(n, (uint64_t)sketch_size);
+    const int use64 = k > 16;
+    if (ns == 0) return fail(AC_E_NO_RECORDS, "did not find sequence records (no hash reached the minimum copy number)");
+    ac_sketch *sk = nullptr;
+    int rc = make_sketch(c, (const unsigned long long *)dev_hashes, dev_counts, ns, k, sketch_size, use64 ? 64 : 32, 0, &sk);
+    if (rc) return rc;
+    k_set_nsketch<<<1, 1, 0, c->s_comp>>>(c->d_jd, (uint32_t)ns);
+    LaunchCtx lc{c->s_comp, &c->launches};
+    SelectBufs tmp = c->sb;
+    tmp.sk_hash = sk->d_hash; tmp.sk_cnt = sk->d_cnt;
+    launch_finalize(lc, tmp, c->d_jd, use64);
+    c->launches += 1;
+    rc = read_jd(c);
+    if (rc) { ac_sketch_free(sk); return rc; }
+    const JobDev &h = *c->h_jd;
+    sk->length = (uint64_t)h.genome_size;
+    if (info) {
+        memset(info, 0, sizeof(*info));
+        info->n_hashes = ns; info->max_hash = h.max_hash; info->sum_counts = h.sum_counts;
+        info->genome_size = h.genome_size; info->coverage = h.coverage; info->hash_bits = use64 ? 64 : 32; info->passes = 1;
+    }
+    *out = sk;
+    return AC_OK;
+}
+
+// ------------------------------------------------------------------ sketches
+extern "C" int ac_sketch_from_hashes(ac_ctx *c, const uint64_t *hashes, uint64_t n, int k, int sketch_size, uint64_t length, ac_sketch **out) {
+    if (!c || !out || (n && !hashes)) return fail(AC_E_PARAM, "ac_sketch_from_hashes: NULL argument");
+    *out = nullptr;
+    if (k < 1 || k > 32) return fail(AC_E_PARAM, "k = %d outside 1..32", k);
+    CK(cudaSetDevice(c->dev));
+    ac_sketch *sk = new ac_sketch();
+    sk->ctx = c; sk->n = n; sk->k = k; sk->s = sketch_size; sk->hash_bits = k > 16 ? 64 : 32; sk->length = length;
+    sk->d_hash = nullptr; sk->d_cnt = nullptr;
+    cudaError_t e = cudaMalloc(&sk->d_hash, (n ? n : 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&sk->d_cnt, (n ? n : 1) * 4);
+    if (e == cudaSuccess && n) e = cudaMemcpy(sk->d_hash, hashes, n * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n) e = cudaMemset(sk->d_cnt, 0, n * 4);
+    if (e != cudaSuccess) { cudaFree(sk->d_hash); cudaFree(sk->d_cnt); delete sk; return fail(AC_E_CUDA, "sketch upload failed: %s", cudaGetErrorString(e)); }
+    *out = sk;
+    return AC_OK;
+}
+extern "C" uint64_t ac_sketch_size(const ac_sketch *sk) { return sk ? sk->n : 0; }
+extern "C" uint64_t ac_sketch_length(const ac_sketch *sk) { return sk ? sk->length : 0; }
+extern "C" int ac_sketch_hashes(const ac_sketch *sk, uint64_t *hashes, uint32_t *counts) {
+    if (!sk) return fail(AC_E_PARAM, "sketch is NULL");
+    CK(cudaSetDevice(sk->ctx->dev));
+    if (sk->n && hashes) CK(cudaMemcpy(hashes, sk->d_hash, sk->n * 8, cudaMemcpyDeviceToHost));
+    if (sk->n && counts) CK(cudaMemcpy(counts, sk->d_cnt, sk->n * 4, cudaMemcpyDeviceToHost));
+    return AC_OK;
+}
+extern "C" void ac_sketch_free(ac_sketch *sk) {
+    if (!sk) return;
+    cudaSetDevice(sk->ctx->dev);
+    cudaFree(sk->d_hash); cudaFree(sk->d_cnt);
+    delete sk;
+}
+
+// ------------------------------------------------------------------ references + dist
+extern "C" int ac_refs_load(ac_ctx *c, const uint64_t *hashes, const uint64_t *offsets, const uint64_t *lengths, int n_refs,
+                            int k, int sketch_size, int hash_bits, ac_refs **out) {
+    if (!c || !out || !offsets || !lengths || n_refs < 0) return fail(AC_E_PARAM, "ac_refs_load: bad argument");
+    *out = nullptr;
+    if (k < 1 || k > 32) return fail(AC_E_PARAM, "k = %d outside 1..32", k);
+    if (hash_bits != 32 && hash_bits != 64) return fail(AC_E_PARAM, "hash_bits = %d", hash_bits);
+    CK(cudaSetDevice(c->dev));
+    const uint64_t total = offsets[n_refs];
+    uint64_t max_n = 0;
+    for (int i = 0; i < n_refs; i++) {
+        if (offsets[i + 1] < offsets[i]) return fail(AC_E_PARAM, "offsets not ascending at %d", i);
+        max_n = std::max<uint64_t>(max_n, offsets[i + 1] - offsets[i]);
+    }
+    ac_refs *r = new ac_refs();
+    r->ctx = c; r->n_refs = n_refs; r->k = k; r->s = sketch_size; r->hash_bits = hash_bits; r->max_n = max_n;
+    r->d_hash = r->d_off = r->d_len = nullptr;
+    cudaError_t e = cudaMalloc(&r->d_hash, (total ? total : 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&r->d_off, (size_t)(n_refs + 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&r->d_len, (size_t)(n_refs ? n_refs : 1) * 8);
+    if (e == cudaSuccess && total) e = cudaMemcpy(r->d_hash, hashes, total * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(r->d_off, offsets, (size_t)(n_refs + 1) * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n_refs) e = cudaMemcpy(r->d_len, lengths, (size_t)n_refs * 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(r->d_hash); cudaFree(r->d_off); cudaFree(r->d_len); delete r; return fail(AC_E_CUDA, "reference upload failed: %s", cudaGetErrorString(e)); }
+    *out = r;
+    return AC_OK;
+}
+extern "C" int ac_refs_count(const ac_refs *r) { return r ? r->n_refs : 0; }
+extern "C" void ac_refs_free(ac_refs *r) {
+    if (!r) return;
+    cudaSetDevice(r->ctx->dev);
+    cudaFree(r->d_hash); cudaFree(r->d_off); cudaFree(r->d_len);
+    delete r;
+}
+
+static int ensure_dist(ac_ctx *c, size_t n_out, size_t n_q) {
+    if (n_out > c->dist_cap) {
+        cudaFree(c->d_dist); cudaFree(c->d_p); cudaFree(c->d_common); cudaFree(c->d_denom);
+        cudaFreeHost(c->h_dist); cudaFreeHost(c->h_p); cudaFreeHost(c->h_common); cudaFreeHost(c->h_denom);
+        c->dist_cap = 0;
+        const size_t cap = std::max<size_t>(n_out, 1024);
+        CK(cudaMalloc(&c->d_dist, cap * 8)); CK(cudaMalloc(&c->d_p, cap * 8));
+        CK(cudaMalloc(&c->d_common, cap * 8)); CK(cudaMalloc(&c->d_denom, cap * 8));
+        CK(cudaHostAlloc(&c->h_dist, cap * 8, cudaHostAllocDefault)); CK(cudaHostAlloc(&c->h_p, cap * 8, cudaHostAllocDefault));
+        CK(cudaHostAlloc(&c->h_common, cap * 8, cudaHostAllocDefault)); CK(cudaHostAlloc(&c->h_denom, cap * 8, cudaHostAllocDefault));
+        c->dist_cap = cap;
+    }
+    if (n_q > c->q_cap) {
+        cudaFree(c->d_qmeta); cudaFreeHost(c->h_qmeta);
+        c->q_cap = 0;
+        const size_t cap = std::max<size_t>(n_q, 64);
+        CK(cudaMalloc(&c->d_qmeta, cap * 3 * 8));
+        CK(cudaHostAlloc(&c->h_qmeta, cap * 3 * 8, cudaHostAllocDefault));
+        c->q_cap = cap;
+    }
+    return AC_OK;
+}
+
+extern "C" int ac_dist_batch(ac_ctx *c, const ac_refs *refs, const ac_sketch *const *queries, int n_q, double *distance,
+                             double *pvalue, uint64_t *common, uint64_t *denom) {
+    if (!c || !refs || !queries || n_q < 0) return fail(AC_E_PARAM, "ac_dist: bad argument");
+    CK(cudaSetDevice(c->dev));
+    const size_t n_out = (size_t)n_q * refs->n_refs;
+    if (n_out == 0) return AC_OK;
+    int rc = ensure_dist(c, n_out, n_q);
+    if (rc) return rc;
+    uint64_t max_q = 0;
+    int s_min = refs->s;
+    for (int i = 0; i < n_q; i++) {
+        const ac_sketch *q = queries[i];
+        if (!q) return fail(AC_E_PARAM, "query %d is NULL", i);
+        if (q->k != refs->k || q->hash_bits != refs->hash_bits)
+            return fail(AC_E_PARAM_MISMATCH, "query sketch k=%d/%d-bit does not match reference k=%d/%d-bit", q->k, q->hash_bits, refs->k, refs->hash_bits);
+        if (q->s != queries[0]->s) return fail(AC_E_PARAM_MISMATCH, "queries of one batch must share the sketch size");
+        c->h_qmeta[i] = (unsigned long long)(uintptr_t)q->d_hash;
+        c->h_qmeta[c->q_cap + i] = q->n;
+        c->h_qmeta[2 * c->q_cap + i] = q->length;
+        max_q = std::max<uint64_t>(max_q, q->n);
+    }
+    s_min = std::min(s_min, queries[0]->s);
+    if (max_q > (1u << 20)) return fail(AC_E_PARAM, "query sketch of %llu hashes exceeds 2^20", (unsigned long long)max_q);
+    CK(cudaMemcpyAsync(c->d_qmeta, c->h_qmeta, c->q_cap * 3 * 8, cudaMemcpyHostToDevice, c->s_comp));
+    LaunchCtx lc{c->s_comp, &c->launches};
+    launch_dist(lc, refs->d_hash, refs->d_off, refs->d_len, refs->n_refs, (const unsigned long long *const *)c->d_qmeta,
+                c->d_qmeta + c->q_cap, c->d_qmeta + 2 * c->q_cap, n_q, refs->k, (unsigned long long)s_min, max_q, c->d_dist,
+                c->d_p, c->d_common, c->d_denom);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_dist, c->d_dist, n_out * 8, cudaMemcpyDeviceToHost, c->s_comp));
+    CK(cudaMemcpyAsync(c->h_p, c->d_p, n_out * 8, cudaMemcpyDeviceToHost, c->s_comp));
+    CK(cudaMemcpyAsync(c->h_common, c->d_common, n_out * 8, cudaMemcpyDeviceToHost, c->s_comp));
+    CK(cudaMemcpyAsync(c->h_denom, c->d_denom, n_out * 8, cudaMemcpyDeviceToHost, c->s_comp));
+    CK(cudaStreamSynchronize(c->s_comp));
+    if (distance) memcpy(distance, c->h_dist, n_out * 8);
+    if (pvalue) memcpy(pvalue, c->h_p, n_out * 8);
+    if (common) memcpy(common, c->h_common, n_out * 8);
+    if (denom) memcpy(denom, c->h_denom, n_out * 8);
+    return AC_OK;
+}
+
+extern "C" int ac_dist(ac_ctx *c, const ac_refs *refs, const ac_sketch *query, double *distance, double *pvalue,
+                       uint64_t *common, uint64_t *denom) {
+    const ac_sketch *q[1] = {query};
+    return ac_dist_batch(c, refs, q, 1, distance, pvalue, common, denom);
+}

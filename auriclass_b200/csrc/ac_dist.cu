@@ -1,0 +1,234 @@
+// ac_dist.cu -- kernel K5: Mash distance + p-value of one query sketch against
+// every reference sketch, plus the integer-issue microbenchmark used as the
+// sketch roofline denominator.
+//
+// Replaces Mash's CommandDistance compareSketches()/pValue() (SURVEY.md section 2.2
+// stages S7-S8, App. A.6) that run inside `mash dist REF QUERY`
+// (auriclass/classes.py:92-104).
+//
+// Mash walks the two ascending lists until `denom` distinct values have been
+// seen (denom capped at the sketch size S).  Equivalent closed form used here:
+//   U = distinct union; denom = min(S, |U|);
+//   common = #{x in R and Q : rank_U(x) <= S},  rank_U(R[i]) = i+1 + lb_Q(R[i]) - c(i),
+//   c(i) = common values before R[i].
+// One CTA per (reference, query) pair: R is consumed in chunks of 1024 consecutive
+// hashes, each thread binary-searches its hash in Q (first in a shared-memory
+// sample of every 64th hash, then inside one 512-byte block), a block scan yields
+// c(i).  Integer compare/merge bound; 24 pairs per AuriClass call.
+#include <math.h>
+
+#include "ac_common.cuh"
+
+namespace ac {
+
+namespace {
+
+typedef unsigned long long u64;
+constexpr int D_THREADS = 1024;
+constexpr int D_SAMPLE = 64;          // Q is sampled every 64th hash into shared memory
+constexpr int D_MAX_SAMPLES = 16384;  // supports |Q| <= 1,048,576 (args.py:126 caps s at 1,000,000)
+
+// ---- binomial tail P(X > k): Loader saddle-point pmf + tail summation (App. A.6; GSL gsl_cdf_binomial_Q in Mash) ----
+__device__ double d_stirlerr(double n) {
+    if (n <= 15.0) {
+        if (n == 0) return 0.0;
+        double f = 1.0;
+        for (int i = 2; i <= (int)n; i++) f *= i;
+        return log(f) - ((n + 0.5) * log(n) - n + 0.918938533204672741780329736406);
+    }
+    const double nn = n * n;
+    if (n > 500) return (1.0 / 12 - (1.0 / 360) / nn) / n;
+    if (n > 80) return (1.0 / 12 - (1.0 / 360 - (1.0 / 1260) / nn) / nn) / n;
+    if (n > 35) return (1.0 / 12 - (1.0 / 360 - (1.0 / 1260 - (1.0 / 1680) / nn) / nn) / nn) / n;
+    return (1.0 / 12 - (1.0 / 360 - (1.0 / 1260 - (1.0 / 1680 - (1.0 / 1188) / nn) / nn) / nn) / nn) / n;
+}
+__device__ double d_bd0(double x, double np) {
+    if (fabs(x - np) < 0.1 * (x + np)) {
+        double v = (x - np) / (x + np), s = (x - np) * v, ej = 2 * x * v;
+        v = v * v;
+        for (int j = 1; j < 1000; j++) {
+            ej *= v;
+            const double s1 = s + ej / (2 * j + 1);
+            if (s1 == s) return s1;
+            s = s1;
+        }
+    }
+    return x * log(x / np) + np - x;
+}
+__device__ double d_log_dbinom(double x, double n, double p) {
+    const double q = 1 - p;
+    if (x == 0) return n * log1p(-p);
+    if (x == n) return n * log(p);
+    const double lc = d_stirlerr(n) - d_stirlerr(x) - d_stirlerr(n - x) - d_bd0(x, n * p) - d_bd0(n - x, n * q);
+    const double lf = 1.837877066409345483560659472811 + log(x) + log1p(-x / n);
+    return lc - 0.5 * lf;
+}
+// P(X > kk), X ~ Binomial(n, p)   (gsl_cdf_binomial_Q(kk, p, n))
+__device__ double d_binomial_Q(u64 kk, double p, u64 n) {
+    if (kk >= n) return 0.0;
+    if (p <= 0) return 0.0;
+    if (p >= 1) return 1.0;
+    const double a = (double)kk + 1, N = (double)n, odds = p / (1 - p);
+    if (a > N * p) {
+        const double lt = d_log_dbinom(a, N, p);
+        if (lt < -745.2) return 0.0;
+        double t = exp(lt), sum = t;
+        for (double i = a; i < N; i += 1) {
+            t *= (N - i) / (i + 1) * odds;
+            sum += t;
+            if (t < sum * 1e-18) break;
+        }
+        return sum;
+    }
+    double t = exp(d_log_dbinom((double)kk, N, p)), sum = t;
+    for (double i = (double)kk; i > 0; i -= 1) {
+        t *= i / (N - i + 1) / odds;
+        sum += t;
+        if (t < sum * 1e-18) break;
+    }
+    return 1.0 - sum;
+}
+
+__global__ void __launch_bounds__(D_THREADS) k5_dist(const u64 *__restrict__ ref_hashes, const u64 *__restrict__ ref_off,
+                                                     const u64 *__restrict__ ref_len, int n_refs,
+                                                     const u64 *const *__restrict__ q_hashes, const u64 *__restrict__ q_n,
+                                                     const u64 *__restrict__ q_len, int k, u64 S, double *__restrict__ o_dist,
+                                                     double *__restrict__ o_p, u64 *__restrict__ o_common,
+                                                     u64 *__restrict__ o_denom) {
+    extern __shared__ u64 s_samp[];  // ceil(max|Q| / 64) hashes (dynamic)
+    __shared__ uint32_t s_w[33];
+    __shared__ unsigned long long s_common_in;
+    const int ri = blockIdx.x % n_refs, qi = blockIdx.x / n_refs;
+    const u64 *R = ref_hashes + ref_off[ri];
+    const uint32_t nR = (uint32_t)(ref_off[ri + 1] - ref_off[ri]);
+    const u64 *Q = q_hashes[qi];
+    const uint32_t nQ = (uint32_t)q_n[qi];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n_samp = (nQ + D_SAMPLE - 1) / D_SAMPLE;  // sample j = Q[j*64]
+    for (uint32_t j = tid; j < n_samp && j < D_MAX_SAMPLES; j += D_THREADS) s_samp[j] = Q[(size_t)j * D_SAMPLE];
+    if (tid == 0) s_common_in = 0;
+    __syncthreads();
+
+    uint32_t carry = 0;          // common values in earlier chunks
+    uint32_t my_common_in = 0;   // common values of this thread with union rank <= S
+    for (uint32_t c0 = 0; c0 < nR; c0 += D_THREADS) {
+        const uint32_t i = c0 + tid;
+        uint32_t lb = 0, isc = 0;
+        u64 x = 0;
+        if (i < nR) {
+            x = R[i];
+            // block search: largest sample index b with s_samp[b] < x  (block b covers Q[b*64 .. b*64+63])
+            uint32_t lo = 0, hi = n_samp;  // first sample >= x in [lo, hi]
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (s_samp[mid] < x) lo = mid + 1; else hi = mid;
+            }
+            // lower bound lies in (Q[(lo-1)*64], Q[lo*64]]
+            uint32_t a = lo ? (lo - 1) * D_SAMPLE + 1 : 0, b = min(nQ, lo * D_SAMPLE);
+            if (lo == n_samp) b = nQ;
+            while (a < b) {
+                const uint32_t mid = (a + b) >> 1;
+                if (Q[mid] < x) a = mid + 1; else b = mid;
+            }
+            lb = a;
+            isc = (lb < nQ && Q[lb] == x) ? 1u : 0u;
+        }
+        uint32_t tot;
+        const uint32_t before = block_excl_sum<D_THREADS>(isc, s_w, tot) + carry;
+        if (isc) {
+            const u64 rank = (u64)i + 1 + lb - before;
+            if (rank <= S) my_common_in++;
+        }
+        carry += tot;
+    }
+    if (my_common_in) atomicAdd(&s_common_in, (unsigned long long)my_common_in);
+    __syncthreads();
+    if (tid == 0) {
+        const u64 uni = (u64)nR + nQ - carry;
+        const u64 denom = uni < S ? uni : S;
+        const u64 common = s_common_in;
+        double d;
+        if (common == denom) d = 0.0;
+        else if (common == 0) d = 1.0;
+        else {
+            const double jac = (double)common / (double)denom;
+            d = -log(2.0 * jac / (1.0 + jac)) / k;
+        }
+        double pv;
+        if (common == 0) pv = 1.0;
+        else {
+            const double space = scalbn(1.0, 2 * k);  // 4^k, exact
+            const double pX = 1.0 / (1.0 + space / (double)ref_len[ri]);
+            const double pY = 1.0 / (1.0 + space / (double)q_len[qi]);
+            const double r = pX * pY / (pX + pY - pX * pY);
+            pv = d_binomial_Q(common - 1, r, denom);
+        }
+        const size_t o = (size_t)qi * n_refs + ri;
+        o_dist[o] = d; o_p[o] = pv; o_common[o] = common; o_denom[o] = denom;
+    }
+}
+
+// ---- integer issue peak: independent IMAD (fma pipe) + LOP3 (alu pipe) chains ----
+__global__ void __launch_bounds__(256) k_int_peak(uint32_t *out, int iters) {
+    uint32_t a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    uint32_t b0 = blockIdx.x, b1 = b0 + 1, b2 = b0 + 2, b3 = b0 + 3, b4 = b0 + 4, b5 = b0 + 5, b6 = b0 + 6, b7 = b0 + 7;
+    const uint32_t m = 0x9E3779B1u, c = 0x7F4A7C15u;
+    for (int i = 0; i < iters; i++) {
+#define STEP(A, B)                                                             \
+    asm volatile("mad.lo.u32 %0, %0, %2, %3;\n\tlop3.b32 %1, %1, %2, %3, 0x96;" \
+                 : "+r"(A), "+r"(B) : "r"(m), "r"(c));
+        STEP(a0, b0) STEP(a1, b1) STEP(a2, b2) STEP(a3, b3) STEP(a4, b4) STEP(a5, b5) STEP(a6, b6) STEP(a7, b7)
+#undef STEP
+    }
+    const uint32_t r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7 ^ b0 ^ b1 ^ b2 ^ b3 ^ b4 ^ b5 ^ b6 ^ b7;
+    if (r == 0x12345678u) out[0] = r;  // never true in practice; keeps the chains alive
+}
+
+}  // namespace
+
+void launch_dist(const LaunchCtx &lc, const unsigned long long *ref_hashes, const unsigned long long *ref_off,
+                 const unsigned long long *ref_len, int n_refs, const unsigned long long *const *q_hashes,
+                 const unsigned long long *q_n, const unsigned long long *q_len, int n_q, int k,
+                 unsigned long long sketch_size, unsigned long long max_q_n, double *d_dist, double *d_p,
+                 unsigned long long *d_common, unsigned long long *d_denom) {
+    if (n_refs <= 0 || n_q <= 0) return;
+    size_t smem = ((max_q_n + D_SAMPLE - 1) / D_SAMPLE) * sizeof(u64);
+    if (smem > (size_t)D_MAX_SAMPLES * sizeof(u64)) smem = (size_t)D_MAX_SAMPLES * sizeof(u64);
+    if (smem < 64) smem = 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k5_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, D_MAX_SAMPLES * (int)sizeof(u64));
+        attr_set = true;
+    }
+    k5_dist<<<n_refs * n_q, D_THREADS, smem, lc.stream>>>(ref_hashes, ref_off, ref_len, n_refs, q_hashes, q_n, q_len, k,
+                                                       sketch_size, d_dist, d_p, d_common, d_denom);
+    ++*lc.launches;
+}
+
+double run_int_peak(const LaunchCtx &lc) {
+    uint32_t *d = nullptr;
+    if (cudaMalloc(&d, 4) != cudaSuccess) return 0.0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int iters = 4096, blocks = sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0, lc.stream);
+        k_int_peak<<<blocks, threads, 0, lc.stream>>>(d, iters);
+        cudaEventRecord(e1, lc.stream);
+        cudaEventSynchronize(e1);
+        ++*lc.launches;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double instr = (double)blocks * threads * (double)iters * 16.0;
+        if (rep > 0 && ms > 0) best = fmax(best, instr / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    return best;
+}
+
+}  // namespace ac

@@ -1,0 +1,372 @@
+// ac_select.cu -- kernels K3 (exact min-copies count filter + bottom-s under a
+// monotonically shrinking threshold) and K4 (genome-size / coverage estimate).
+//
+// Replaces Mash's MinHashHeap::tryInsert / hashesPending bookkeeping and
+// estimateSetSize / estimateMultiplicity (SURVEY.md section 2.2 stages S4-S5,
+// App. A.4/A.5) that run inside `mash sketch -r -m M`
+// (auriclass/classes.py:576-596).
+//
+// State: a table of every distinct hash <= tau seen so far with its exact
+// occurrence count, sorted ascending.  A consolidation folds the candidate buffer
+// (hash occurrences <= tau emitted by K2 since the last one) into the table:
+//   LSD radix sort of (hash,count) pairs -> run-length sums -> count >= m scan
+//   -> if >= s qualified entries exist, tau drops to the s-th of them and the
+//   table is truncated there.
+// Entries above the s-th qualified hash can never enter the sketch (App. A.4), so
+// tau only ever shrinks and counts of everything <= tau stay exact.
+#include "ac_common.cuh"
+
+namespace ac {
+
+namespace {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per CTA
+
+typedef unsigned long long u64;
+
+// ------------------------------------------------------------- radix sort
+__global__ void __launch_bounds__(RS_THREADS) rs_hist(const u64 *__restrict__ keys, uint32_t n, int shift,
+                                                      uint32_t *__restrict__ hist, uint32_t n_tiles) {
+    __shared__ uint32_t h[256];
+    const uint32_t tid = threadIdx.x, tile = blockIdx.x;
+    h[tid] = 0;
+    __syncthreads();
+    const uint32_t base = tile * RS_TILE;
+#pragma unroll 4
+    for (int i = 0; i < RS_ITEMS; i++) {
+        const uint32_t idx = base + i * RS_THREADS + tid;
+        if (idx < n) atomicAdd(&h[(uint32_t)(keys[idx] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[tid * n_tiles + tile] = h[tid];
+}
+
+// one CTA per digit: exclusive scan of the digit's row over tiles, row total -> totals[digit]
+__global__ void __launch_bounds__(RS_THREADS) rs_scan_rows(uint32_t *__restrict__ hist, uint32_t n_tiles,
+                                                           uint32_t *__restrict__ totals) {
+    __shared__ uint32_t s_w[33];
+    uint32_t *row = hist + (size_t)blockIdx.x * n_tiles;
+    uint32_t carry = 0;
+    for (uint32_t b = 0; b < n_tiles; b += RS_THREADS) {
+        const uint32_t i = b + threadIdx.x;
+        const uint32_t v = (i < n_tiles) ? row[i] : 0u;
+        uint32_t tot;
+        const uint32_t ex = block_excl_sum<RS_THREADS>(v, s_w, tot);
+        if (i < n_tiles) row[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) totals[blockIdx.x] = carry;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter(const u64 *__restrict__ kin, const uint32_t *__restrict__ vin,
+                                                         u64 *__restrict__ kout, uint32_t *__restrict__ vout,
+                                                         uint32_t n, int shift, const uint32_t *__restrict__ hist,
+                                                         const uint32_t *__restrict__ totals, uint32_t n_tiles) {
+    __shared__ uint32_t s_cnt[RS_THREADS / 32][256];
+    __shared__ uint32_t s_gofs[256];
+    __shared__ uint32_t s_w[33];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tile = blockIdx.x;
+#pragma unroll
+    for (int w = 0; w < RS_THREADS / 32; w++) s_cnt[w][tid] = 0;
+    uint32_t tot;
+    const uint32_t dbase = block_excl_sum<RS_THREADS>(totals[tid], s_w, tot);  // syncs
+    s_gofs[tid] = dbase + hist[tid * n_tiles + tile];
+    __syncthreads();
+
+    const uint32_t base = tile * RS_TILE + warp * (32 * RS_ITEMS);
+    u64 key[RS_ITEMS];
+    uint32_t rk[RS_ITEMS];
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        const uint32_t idx = base + i * 32 + lane;
+        const bool valid = idx < n;
+        key[i] = valid ? kin[idx] : 0ULL;
+        const uint32_t d = valid ? ((uint32_t)(key[i] >> shift) & 255u) : (256u + lane);
+        const uint32_t peers = __match_any_sync(FULL, d);
+        const uint32_t r = __popc(peers & lt);
+        const uint32_t prev = valid ? s_cnt[warp][d] : 0u;
+        __syncwarp();
+        if (valid && r == 0) s_cnt[warp][d] = prev + __popc(peers);
+        __syncwarp();
+        rk[i] = prev + r;
+    }
+    __syncthreads();
+    {   // exclusive prefix of the per-warp digit counts across warps (thread = digit)
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; w++) {
+            const uint32_t c = s_cnt[w][tid];
+            s_cnt[w][tid] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        const uint32_t idx = base + i * 32 + lane;
+        if (idx < n) {
+            const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+            const uint32_t pos = s_gofs[d] + s_cnt[warp][d] + rk[i];
+            kout[pos] = key[i];
+            vout[pos] = vin[idx];
+        }
+    }
+}
+
+// sorts n (key,val) pairs by the low key_bits of the key; returns 0 if the result is in (ka,va), 1 if in (kb,vb)
+int radix_sort_pairs(const LaunchCtx &lc, u64 *ka, uint32_t *va, u64 *kb, uint32_t *vb, uint32_t n, int key_bits,
+                     uint32_t *hist, uint32_t *totals) {
+    if (n == 0) return 0;
+    const uint32_t n_tiles = div_up(n, RS_TILE);
+    const int passes = (key_bits + 7) / 8;
+    int cur = 0;
+    for (int p = 0; p < passes; p++) {
+        const u64 *kin = cur ? kb : ka; const uint32_t *vin = cur ? vb : va;
+        u64 *kout = cur ? ka : kb; uint32_t *vout = cur ? va : vb;
+        rs_hist<<<n_tiles, RS_THREADS, 0, lc.stream>>>(kin, n, 8 * p, hist, n_tiles);
+        rs_scan_rows<<<256, RS_THREADS, 0, lc.stream>>>(hist, n_tiles, totals);
+        rs_scatter<<<n_tiles, RS_THREADS, 0, lc.stream>>>(kin, vin, kout, vout, n, 8 * p, hist, totals, n_tiles);
+        *lc.launches += 3;
+        cur ^= 1;
+    }
+    return cur;
+}
+
+// ------------------------------------------------------- consolidation
+// vals of the fresh candidates are an implicit 1; table entries are appended behind them
+__global__ void k3_prepare(u64 *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t n_cand,
+                           const u64 *__restrict__ tab_hash, const uint32_t *__restrict__ tab_cnt, uint32_t n_table) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_cand) vals[i] = 1u;
+    else if (i < n_cand + n_table) { keys[i] = tab_hash[i - n_cand]; vals[i] = tab_cnt[i - n_cand]; }
+}
+
+constexpr int SC_THREADS = 256;
+constexpr int SC_ITEMS = 8;
+constexpr int SC_TILE = SC_THREADS * SC_ITEMS;  // 2048 elements per CTA, thread owns 8 consecutive
+
+// pass 1 over the sorted pairs: per tile (#run heads, sum of vals)
+__global__ void __launch_bounds__(SC_THREADS) k3_runs_reduce(const u64 *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                             uint32_t n, uint32_t *__restrict__ tile_heads,
+                                                             uint32_t *__restrict__ tile_vals) {
+    __shared__ uint32_t s_w[33];
+    const uint32_t base = blockIdx.x * SC_TILE + threadIdx.x * SC_ITEMS;
+    uint32_t heads = 0, vs = 0;
+    u64 prev = (base > 0 && base - 1 < n) ? keys[base - 1] : 0ULL;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; i++) {
+        const uint32_t idx = base + i;
+        if (idx < n) {
+            const u64 k = keys[idx];
+            heads += (idx == 0 || k != prev) ? 1u : 0u;
+            vs += vals[idx];
+            prev = k;
+        }
+    }
+    uint32_t th, tv;
+    block_excl_sum<SC_THREADS>(heads, s_w, th);
+    block_excl_sum<SC_THREADS>(vs, s_w, tv);
+    if (threadIdx.x == 0) { tile_heads[blockIdx.x] = th; tile_vals[blockIdx.x] = tv; }
+}
+
+// single CTA: exclusive scan of the two tile arrays in place; totals -> jd (mode 0) or qualified count (mode 1)
+__global__ void __launch_bounds__(1024) k3_scan_tiles(uint32_t *__restrict__ a, uint32_t *__restrict__ b, uint32_t n_tiles,
+                                                      JobDev *__restrict__ jd, uint32_t *__restrict__ start_sum, int mode,
+                                                      uint32_t sketch_size) {
+    __shared__ uint32_t s_w[33];
+    uint32_t ca = 0, cb = 0;
+    for (uint32_t t0 = 0; t0 < n_tiles; t0 += 1024) {
+        const uint32_t i = t0 + threadIdx.x;
+        const uint32_t va = (i < n_tiles) ? a[i] : 0u;
+        const uint32_t vb = (b && i < n_tiles) ? b[i] : 0u;
+        uint32_t ta, tb;
+        const uint32_t ea = block_excl_sum<1024>(va, s_w, ta);
+        const uint32_t eb = block_excl_sum<1024>(vb, s_w, tb);
+        if (i < n_tiles) { a[i] = ca + ea; if (b) b[i] = cb + eb; }
+        ca += ta; cb += tb;
+    }
+    if (threadIdx.x == 0) {
+        if (mode == 0) {
+            jd->n_unique = ca;
+            jd->total_vals = cb;
+            start_sum[ca] = cb;  // sentinel: exclusive prefix one past the last unique key
+        } else {
+            jd->n_qualified = ca;
+            jd->n_sketch = ca < sketch_size ? ca : sketch_size;
+            jd->n_table = jd->n_unique;  // default: keep everything (k3_qual_apply lowers it with tau)
+            jd->cand_count = 0;
+        }
+    }
+}
+
+// pass 2: unique keys -> tab_hash, exclusive val prefix at each run head -> start_sum
+__global__ void __launch_bounds__(SC_THREADS) k3_runs_apply(const u64 *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                            uint32_t n, const uint32_t *__restrict__ tile_heads,
+                                                            const uint32_t *__restrict__ tile_vals, u64 *__restrict__ tab_hash,
+                                                            uint32_t *__restrict__ start_sum) {
+    __shared__ uint32_t s_w[33];
+    const uint32_t base = blockIdx.x * SC_TILE + threadIdx.x * SC_ITEMS;
+    u64 k[SC_ITEMS];
+    uint32_t v[SC_ITEMS];
+    uint32_t heads = 0, vs = 0;
+    const u64 before = (base > 0 && base - 1 < n) ? keys[base - 1] : 0ULL;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; i++) {
+        const uint32_t idx = base + i;
+        k[i] = (idx < n) ? keys[idx] : 0ULL;
+        v[i] = (idx < n) ? vals[idx] : 0u;
+    }
+    u64 prev = before;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; i++) {
+        const uint32_t idx = base + i;
+        if (idx < n) { heads += (idx == 0 || k[i] != prev) ? 1u : 0u; vs += v[i]; prev = k[i]; }
+    }
+    uint32_t th, tv;
+    uint32_t eh = block_excl_sum<SC_THREADS>(heads, s_w, th) + tile_heads[blockIdx.x];
+    uint32_t ev = block_excl_sum<SC_THREADS>(vs, s_w, tv) + tile_vals[blockIdx.x];
+    prev = before;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; i++) {
+        const uint32_t idx = base + i;
+        if (idx < n) {
+            if (idx == 0 || k[i] != prev) { tab_hash[eh] = k[i]; start_sum[eh] = ev; eh++; }
+            ev += v[i];
+            prev = k[i];
+        }
+    }
+}
+
+// pass 3 over unique keys: qualified (count >= m) count per tile
+__global__ void __launch_bounds__(SC_THREADS) k3_qual_reduce(const uint32_t *__restrict__ start_sum,
+                                                             const JobDev *__restrict__ jd, uint32_t min_copies,
+                                                             uint32_t *__restrict__ tile_q) {
+    __shared__ uint32_t s_w[33];
+    const uint32_t n = jd->n_unique;
+    const uint32_t base = blockIdx.x * SC_TILE + threadIdx.x * SC_ITEMS;
+    uint32_t q = 0;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; i++) {
+        const uint32_t u = base + i;
+        if (u < n) q += (start_sum[u + 1] - start_sum[u] >= min_copies) ? 1u : 0u;
+    }
+    uint32_t tq;
+    block_excl_sum<SC_THREADS>(q, s_w, tq);
+    if (threadIdx.x == 0) tile_q[blockIdx.x] = tq;
+}
+
+// pass 4: counts -> tab_cnt, qualified prefix -> sketch, s-th qualified -> tau + table truncation.
+// compact != 0 (multi-GPU owner merge): write ALL qualified entries to (out_hash,out_cnt) instead.
+__global__ void __launch_bounds__(SC_THREADS) k3_qual_apply(const u64 *__restrict__ tab_hash, const uint32_t *__restrict__ start_sum,
+                                                            uint32_t *__restrict__ tab_cnt, JobDev *__restrict__ jd,
+                                                            uint32_t min_copies, uint32_t sketch_size,
+                                                            const uint32_t *__restrict__ tile_q, u64 *__restrict__ out_hash,
+                                                            uint32_t *__restrict__ out_cnt, int compact) {
+    __shared__ uint32_t s_w[33];
+    const uint32_t n = jd->n_unique;
+    const uint32_t base = blockIdx.x * SC_TILE + threadIdx.x * SC_ITEMS;
+    uint32_t cnt[SC_ITEMS];
+    uint32_t q = 0;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; i++) {
+        const uint32_t u = base + i;
+        cnt[i] = (u < n) ? (start_sum[u + 1] - start_sum[u]) : 0u;
+        q += (u < n && cnt[i] >= min_copies) ? 1u : 0u;
+    }
+    uint32_t tq;
+    uint32_t rank = block_excl_sum<SC_THREADS>(q, s_w, tq) + tile_q[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; i++) {
+        const uint32_t u = base + i;
+        if (u < n) {
+            if (!compact) tab_cnt[u] = cnt[i];
+            if (cnt[i] >= min_copies) {
+                if (compact || rank < sketch_size) { out_hash[rank] = tab_hash[u]; out_cnt[rank] = cnt[i]; }
+                if (!compact && rank + 1 == sketch_size) { jd->tau = tab_hash[u]; jd->n_table = u + 1; }
+                rank++;
+            }
+        }
+    }
+}
+
+// K4: estimates from the finished sketch (Mash estimateSetSize / multiplicity; App. A.5)
+__global__ void __launch_bounds__(1024) k4_finalize(const u64 *__restrict__ sk_hash, const uint32_t *__restrict__ sk_cnt,
+                                                    JobDev *__restrict__ jd, int use64) {
+    __shared__ unsigned long long s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    const uint32_t n = jd->n_sketch;
+    unsigned long long local = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += 1024) local += sk_cnt[i];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) local += __shfl_xor_sync(FULL, local, d);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_sum, local);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (n) {
+            const u64 mx = sk_hash[n - 1];
+            const double space = use64 ? 18446744073709551616.0 : 4294967296.0;
+            jd->max_hash = mx;
+            jd->sum_counts = s_sum;
+            jd->genome_size = space * (double)n / (double)mx;
+            jd->coverage = (double)s_sum / (double)n;
+        } else {
+            jd->max_hash = 0; jd->sum_counts = 0; jd->genome_size = 0.0; jd->coverage = 0.0;
+        }
+    }
+}
+
+void runs_and_qualify(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, const u64 *keys, const uint32_t *vals,
+                      uint32_t n, int sketch_size, int min_copies, u64 *out_hash, uint32_t *out_cnt, int compact) {
+    const uint32_t n_tiles = div_up(n ? n : 1, SC_TILE);
+    uint32_t *t_heads = sb.tile_tmp, *t_vals = sb.tile_tmp + n_tiles;
+    k3_runs_reduce<<<n_tiles, SC_THREADS, 0, lc.stream>>>(keys, vals, n, t_heads, t_vals);
+    k3_scan_tiles<<<1, 1024, 0, lc.stream>>>(t_heads, t_vals, n_tiles, jd, sb.start_sum, 0, 0);
+    k3_runs_apply<<<n_tiles, SC_THREADS, 0, lc.stream>>>(keys, vals, n, t_heads, t_vals, sb.tab_hash, sb.start_sum);
+    k3_qual_reduce<<<n_tiles, SC_THREADS, 0, lc.stream>>>(sb.start_sum, jd, (uint32_t)min_copies, t_heads);
+    k3_scan_tiles<<<1, 1024, 0, lc.stream>>>(t_heads, nullptr, n_tiles, jd, sb.start_sum, 1, (uint32_t)sketch_size);
+    k3_qual_apply<<<n_tiles, SC_THREADS, 0, lc.stream>>>(sb.tab_hash, sb.start_sum, sb.tab_cnt, jd, (uint32_t)min_copies,
+                                                         (uint32_t)sketch_size, t_heads, out_hash, out_cnt, compact);
+    *lc.launches += 6;
+}
+
+}  // namespace
+
+void launch_consolidate(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, uint64_t n_cand, uint32_t n_table,
+                        int key_bits, int sketch_size, int min_copies) {
+    const uint32_t n = (uint32_t)n_cand + n_table;
+    k3_prepare<<<div_up(n ? n : 1, 256), 256, 0, lc.stream>>>(sb.keys_a, sb.vals_a, (uint32_t)n_cand, sb.tab_hash,
+                                                              sb.tab_cnt, n_table);
+    ++*lc.launches;
+    const int where = radix_sort_pairs(lc, sb.keys_a, sb.vals_a, sb.keys_b, sb.vals_b, n, key_bits, sb.hist,
+                                       sb.hist + (size_t)256 * div_up(n ? n : 1, RS_TILE));
+    const u64 *keys = where ? sb.keys_b : sb.keys_a;
+    const uint32_t *vals = where ? sb.vals_b : sb.vals_a;
+    runs_and_qualify(lc, sb, jd, keys, vals, n, sketch_size, min_copies, sb.sk_hash, sb.sk_cnt, 0);
+}
+
+void launch_finalize(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, int use64) {
+    k4_finalize<<<1, 1024, 0, lc.stream>>>(sb.sk_hash, sb.sk_cnt, jd, use64);
+    ++*lc.launches;
+}
+
+void launch_merge_counts(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, uint64_t n, int min_copies) {
+    const int where = radix_sort_pairs(lc, sb.keys_a, sb.vals_a, sb.keys_b, sb.vals_b, (uint32_t)n, 64, sb.hist,
+                                       sb.hist + (size_t)256 * div_up(n ? n : 1, RS_TILE));
+    const u64 *keys = where ? sb.keys_b : sb.keys_a;
+    const uint32_t *vals = where ? sb.vals_b : sb.vals_a;
+    // qualified entries are compacted into the buffer pair that does not hold the sorted input
+    u64 *oh = where ? sb.keys_a : sb.keys_b;
+    uint32_t *oc = where ? sb.vals_a : sb.vals_b;
+    runs_and_qualify(lc, sb, jd, keys, vals, (uint32_t)n, 0x7fffffff, min_copies, oh, oc, 1);
+    if (oh != sb.keys_a) {
+        // results are expected in keys_a/vals_a: n_qualified <= n entries
+        cudaMemcpyAsync(sb.keys_a, oh, n * sizeof(u64), cudaMemcpyDeviceToDevice, lc.stream);
+        cudaMemcpyAsync(sb.vals_a, oc, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, lc.stream);
+    }
+}
+
+}  // namespace ac

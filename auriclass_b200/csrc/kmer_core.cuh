@@ -1,0 +1,229 @@
+// kmer_core.cuh -- per-thread canonical k-mer + MurmurHash3_x64_128 core of kernel K2.
+//
+// Replaces Mash's Sketch.cpp addMinHashes()/getHash() (external binary called at
+// auriclass/classes.py:576-596 and :696-713; algorithm: SURVEY.md App. A.3).
+// Everything here is __host__ __device__ so tests/test_core_host.py can run the
+// very same arithmetic on the CPU (through csrc/hostcheck.cpp) against the oracle;
+// the product path only ever calls it from device code.
+//
+// Data model.  K1 hands K2 a *sanitised compacted base stream* Z: one byte per
+// sequence character, upper-case 'A','C','G','T' for valid bases, 0x00 for a
+// record separator and 0x01 for any other character.  Valid bytes all have bit 6
+// set, invalid ones do not.  A thread owns W consecutive window starts and holds
+// its run of W+K-1 bytes as little-endian 32-bit words r[0..RW).  The k-mer ASCII
+// words MurmurHash3 needs are then byte-granular *slices* of r (forward strand)
+// and of q = reverse(complement(r)) (reverse strand): one PRMT per word, no
+// rolling state and no 2-bit <-> ASCII expansion.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define AC_HD __host__ __device__ __forceinline__
+#else
+#define AC_HD inline
+#endif
+
+namespace ackmer {
+
+AC_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        uint32_t s = (sel >> (4 * i)) & 0xF;
+        uint32_t byte = (uint32_t)(v >> (8 * (s & 7))) & 0xFF;
+        if (s & 8) byte = (byte & 0x80) ? 0xFF : 0;
+        r |= byte << (8 * i);
+    }
+    return r;
+#endif
+}
+
+AC_HD uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+
+AC_HD uint64_t fmix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+
+// word j of a K-byte key held as NW little-endian words, 0 beyond the key
+template <int K, int J>
+AC_HD uint32_t key_word(const uint32_t *w) {
+    if constexpr (J < (K + 3) / 4) return w[J]; else return 0u;
+}
+
+// h1 of MurmurHash3_x64_128(key, K, seed).  w[] = the K key bytes as (K+3)/4
+// little-endian words, bytes past K in the last word MUST be zero.
+// Mash: hash = first 8 bytes of the 128-bit digest = h1.
+template <int K>
+AC_HD uint64_t murmur3_h1(const uint32_t *w, uint32_t seed) {
+    const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+    uint64_t h1 = seed, h2 = seed;
+    constexpr int NB = K / 16;
+    if constexpr (NB >= 1) {
+        uint64_t k1 = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+        uint64_t k2 = (uint64_t)w[2] | ((uint64_t)w[3] << 32);
+        k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+        k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+    }
+    if constexpr (NB >= 2) {
+        uint64_t k1 = (uint64_t)w[4] | ((uint64_t)w[5] << 32);
+        uint64_t k2 = (uint64_t)w[6] | ((uint64_t)w[7] << 32);
+        k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+        k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+    }
+    constexpr int T = K & 15;
+    if constexpr (T > 8) {
+        uint64_t k2 = (uint64_t)key_word<K, 4 * NB + 2>(w) | ((uint64_t)key_word<K, 4 * NB + 3>(w) << 32);
+        k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+    }
+    if constexpr (T > 0) {
+        uint64_t k1 = (uint64_t)key_word<K, 4 * NB>(w) | ((uint64_t)key_word<K, 4 * NB + 1>(w) << 32);
+        k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+    }
+    h1 ^= (uint64_t)K; h2 ^= (uint64_t)K;
+    h1 += h2; h2 += h1;
+    h1 = fmix64(h1); h2 = fmix64(h2);
+    h1 += h2;
+    return h1;
+}
+
+// SWAR complement of four sanitised bases: A(41)<->T(54) differ by 0x15,
+// C(43)<->G(47) by 0x04; bit 1 of the byte tells the pair.
+AC_HD uint32_t comp4(uint32_t w) {
+    uint32_t b = (w >> 1) & 0x01010101u;
+    return w ^ (0x15151515u ^ (b * 0x11u));
+}
+
+// bit j of the result = byte j of w is a valid base (bit 6 set)
+AC_HD uint32_t valid_nibble(uint32_t w) {
+    uint32_t t = (w >> 6) & 0x01010101u;
+    return (t * 0x01020408u) >> 24;
+}
+
+template <int K, int W>
+struct RunCfg {
+    static constexpr int RUN_BYTES = W + K - 1;             // bytes the W windows touch
+    static constexpr int RW = 4 * ((W + K + 15) / 16);      // words held per thread (16-byte loads); >= W+K bytes so
+                                                            // K2's record statistics can look K bytes back from byte K+W-1
+    static constexpr int NW = (K + 3) / 4;                  // words per k-mer
+    static_assert(4 * RW <= 64, "validity mask is 64 bits");
+    static_assert(W <= 32, "window mask is 32 bits");
+};
+
+// bit i of the result: bytes i .. i+K-1 of the run are all valid
+template <int K>
+AC_HD uint64_t windows_all_valid(uint64_t m) {
+    uint64_t p[6];
+    p[0] = m;
+    p[1] = p[0] & (p[0] >> 1);
+    p[2] = p[1] & (p[1] >> 2);
+    p[3] = p[2] & (p[2] >> 4);
+    p[4] = p[3] & (p[3] >> 8);
+    p[5] = p[4] & (p[4] >> 16);
+    uint64_t res = ~0ULL;
+    int off = 0;
+#pragma unroll
+    for (int b = 5; b >= 0; b--) {
+        if ((K >> b) & 1) { res &= p[b] >> off; off += 1 << b; }
+    }
+    return res;
+}
+
+// word j (bytes off+4j .. off+4j+3) of the byte string held in words a[]
+template <int OFF>
+AC_HD uint32_t slice_word(const uint32_t *a) {
+    constexpr int wi = OFF >> 2, sh = OFF & 3;
+    if constexpr (sh == 0) return a[wi];
+    else if constexpr (sh == 1) return byte_perm(a[wi], a[wi + 1], 0x4321);
+    else if constexpr (sh == 2) return byte_perm(a[wi], a[wi + 1], 0x5432);
+    else return byte_perm(a[wi], a[wi + 1], 0x6543);
+}
+
+template <int K, int OFF, int J, int NW>
+AC_HD void slice_key(const uint32_t *a, uint32_t *out) {
+    if constexpr (J < NW) {
+        uint32_t v;
+        if constexpr (J == NW - 1 && (K & 3) != 0) {
+            // last word: only K&3 bytes belong to the key; avoid reading a[wi+1] past the run
+            constexpr int o = OFF + 4 * J, wi = o >> 2, sh = o & 3, nb = K & 3;
+            if constexpr (sh + nb <= 4) v = (a[wi] >> (8 * sh)) & ((1u << (8 * nb)) - 1u);
+            else v = slice_word<o>(a) & ((1u << (8 * nb)) - 1u);
+        } else {
+            v = slice_word<OFF + 4 * J>(a);
+        }
+        out[J] = v;
+        slice_key<K, OFF, J + 1, NW>(a, out);
+    }
+}
+
+// true when the reverse-complement key c sorts strictly before the forward key f
+// (memcmp order over the K ASCII bytes).
+template <int NW>
+AC_HD bool rc_is_smaller(const uint32_t *f, const uint32_t *c) {
+    // big-endian view of the first word decides unless the first 4 bases tie
+    uint32_t fb = byte_perm(f[0], 0, 0x0123), cb = byte_perm(c[0], 0, 0x0123);
+    if (fb != cb) return cb < fb;
+#pragma unroll
+    for (int j = 1; j < NW; j++) {
+        fb = byte_perm(f[j], 0, 0x0123); cb = byte_perm(c[j], 0, 0x0123);
+        if (fb != cb) return cb < fb;
+    }
+    return false;
+}
+
+template <int K, int W, int I, class Emit>
+AC_HD void process_window(const uint32_t *r, const uint32_t *q, uint32_t vmask, uint32_t seed, Emit &emit) {
+    if constexpr (I < W) {
+        using C = RunCfg<K, W>;
+        if ((vmask >> I) & 1u) {
+            uint32_t f[C::NW], c[C::NW];
+            slice_key<K, I, 0, C::NW>(r, f);
+            slice_key<K, 4 * C::RW - K - I, 0, C::NW>(q, c);
+            const bool use_rc = rc_is_smaller<C::NW>(f, c);
+            uint32_t key[C::NW];
+#pragma unroll
+            for (int j = 0; j < C::NW; j++) key[j] = use_rc ? c[j] : f[j];
+            emit(I, murmur3_h1<K>(key, seed));
+        }
+        process_window<K, W, I + 1, Emit>(r, q, vmask, seed, emit);
+    }
+}
+
+// Hash every valid window of one thread's run.  r[RW]: run bytes as LE words
+// (bytes past the run may hold anything; they only enter windows >= W).
+// win_ok: bit i set when window i may be emitted (range clipping by the caller).
+// emit(i, h1) is called for each surviving window; returns the window mask.
+template <int K, int W, class Emit>
+AC_HD uint32_t process_run(const uint32_t *r, uint32_t win_ok, uint32_t seed, Emit &emit) {
+    using C = RunCfg<K, W>;
+    uint64_t m = 0;
+#pragma unroll
+    for (int j = 0; j < C::RW; j++) m |= (uint64_t)valid_nibble(r[j]) << (4 * j);
+    uint32_t vmask = (uint32_t)windows_all_valid<K>(m) & win_ok;
+    if (W < 32) vmask &= (1u << (W & 31)) - 1u;
+    if (vmask == 0) return 0;
+    uint32_t q[C::RW];
+#pragma unroll
+    for (int j = 0; j < C::RW; j++) q[j] = byte_perm(comp4(r[C::RW - 1 - j]), 0, 0x0123);
+    process_window<K, W, 0, Emit>(r, q, vmask, seed, emit);
+    return vmask;
+}
+
+// K1's per-byte sanitiser (scalar form; the kernel uses it per byte of a word).
+// valid ACGTacgt -> upper case, everything else -> 0x01.
+AC_HD uint32_t sanitise_byte(uint32_t c) {
+    const uint32_t u = c & 0xDFu;
+    const bool ok = ((c & 0xC0u) == 0x40u) && ((0x0010008Au >> (c & 0x1Fu)) & 1u);
+    return ok ? u : 0x01u;
+}
+
+}  // namespace ackmer

@@ -1,0 +1,347 @@
+"""Parity of the CUDA path (through the C ABI, via ctypes) with the oracle and the reference's
+golden vectors.  Bit-exact for hashes, counts, shared-hash counts; distances / p-values within
+1e-12 relative (north_star).  Needs a B200: run with `-m gpu`."""
+import gzip
+import json
+
+import numpy as np
+import pytest
+
+from auriclass_b200 import _lib, synth
+from auriclass_b200._lib import AC_MODE_FASTA, AC_MODE_READS
+from auriclass_b200.msh import read_msh
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+D = "tests/data/"
+REL = 1e-12  # relative tolerance for distance / p-value / estimates computed in double on the device
+
+
+def rel_close(a, b, tol=REL):
+    return a == b or abs(a - b) <= tol * max(abs(a), abs(b))
+
+
+def assert_same_sketch(sk, ref):
+    h, c = sk.hashes()
+    assert len(h) == len(ref.hashes)
+    assert np.array_equal(h, ref.hashes)
+    assert np.array_equal(c, ref.counts)
+    assert sk.info["n_kmers"] == ref.n_kmers
+    assert sk.info["n_kept"] == ref.n_kept
+    assert sk.info["total_len"] == ref.total_len
+    if len(h):
+        assert sk.genome_size == ref.genome_size  # same IEEE operations on both sides
+        assert sk.coverage == ref.coverage
+
+
+@pytest.fixture(scope="module")
+def ref_msh():
+    return read_msh(D + "ref_sketch.msh")
+
+
+@pytest.fixture(scope="module")
+def reads():
+    return [oracle.read_maybe_gz(D + "NC_001416.1_1.fq.gz"), oracle.read_maybe_gz(D + "NC_001416.1_2.fq.gz")]
+
+
+# ------------------------------------------------------------------ reference-pinned vectors
+@pytest.mark.parametrize("fasta,idx", [("NC_001416.1.fasta.gz", 0), ("NC_001604.1.fasta.gz", 1)])
+def test_fasta_sketch_equals_mash_sketch_file(engine, ref_msh, fasta, idx):
+    sk = engine.sketch_fasta(D + fasta, k=27, s=50000)
+    h, _ = sk.hashes()
+    assert np.array_equal(h, ref_msh.references[idx].hashes)  # mash's own hash list, bit for bit
+    assert sk.length == ref_msh.references[idx].length
+    assert_same_sketch(sk, oracle.sketch([oracle.read_maybe_gz(D + fasta)], 27, 50000, 1))
+
+
+def test_fastq_min_copies_golden(engine, ref_msh, reads):
+    sk = engine.sketch_reads([D + "NC_001416.1_1.fq.gz", D + "NC_001416.1_2.fq.gz"], k=27, s=50000, m=3)
+    assert_same_sketch(sk, oracle.sketch(reads, 27, 50000, 3))
+    assert len(sk) == 48451 and "%g" % sk.genome_size == "48454.7"
+    rows = engine.dist(engine.load_references(D + "ref_sketch.msh"), sk)
+    assert [(r.common, r.denom) for r in rows] == [(48451, 48476), (0, 50000)]
+    assert "%g" % rows[0].distance == "9.55405e-06" and "%g" % rows[0].pvalue == "0"
+    assert rows[1].distance == 1.0 and rows[1].pvalue == 1.0
+
+
+def test_workflow_methods_reproduce_reference_dicts(engine):
+    # same calls and assertions as /root/reference/tests/test_correct_workflow.py:86-105 and :184-203
+    from pathlib import Path
+
+    from auriclass_b200.workflow import FastaMashWorkflow, FastqMashWorkflow
+    golden = json.load(open("tests/golden/workflow_dicts.json"))
+
+    def as_int_keys(d):
+        return {k: {int(i): v for i, v in col.items()} for k, col in d.items()}
+
+    fq = FastqMashWorkflow("test", ["tests/data/NC_001416.1_1.fq.gz", "tests/data/NC_001416.1_2.fq.gz"],
+                           "tests/data/ref_sketch.msh", 27, 50_000, 3, "tests/data/clade_config.csv")
+    fq.query_sketch_path = Path("tmp_data/tmpfile.msh")
+    fq.sketch_fastq_query()
+    fq.run_mash_dist()
+    assert fq.mash_output.to_dict() == as_int_keys(golden["mash_output_to_dict_fastq"])
+    assert fq.estimated_genome_size == golden["fastq_estimated_genome_size"]
+    assert fq.mash_output.sort_values("Distance")["Distance"].iloc[0] == golden["fastq_minimal_distance"]
+
+    fa = FastaMashWorkflow("test", ["tests/data/NC_001416.1.fasta.gz"], "tests/data/ref_sketch.msh", 27, 50_000, 3,
+                           "tests/data/clade_config.csv")
+    fa.query_sketch_path = Path("tmp_data/tmpfile.msh")
+    fa.sketch_fasta_query()
+    fa.run_mash_dist()
+    assert fa.mash_output.to_dict() == as_int_keys(golden["mash_output_to_dict_fasta"])
+    assert fa.get_error_bounds() == open("tests/golden/mash_bounds_k27_p0.99.txt").read()
+
+
+def test_empty_fastq_raises_like_mash(engine):
+    # /root/reference/tests/test_failing_workflow.py:51-77
+    from auriclass_b200.workflow import FastqMashWorkflow
+    with pytest.raises(_lib.NoRecordsError):
+        engine.sketch_reads([D + "test_empty_1.fq.gz", D + "test_empty_2.fq.gz"], k=27, s=50000, m=3)
+    wf = FastqMashWorkflow("t", [D + "test_empty_1.fq.gz", D + "test_empty_2.fq.gz"], D + "ref_sketch.msh", 27, 50000, 3,
+                           D + "clade_config.csv")
+    with pytest.raises(ValueError, match="Did not find sequence records"):
+        wf.sketch_fastq_query()
+
+
+# ------------------------------------------------------------------ derived vectors
+@pytest.mark.parametrize("files,m,s", [((0, 1), 1, 50000), ((0, 1), 3, 1000), ((0, 1), 2, 1000), ((0, 1), 1, 1000),
+                                       ((0,), 3, 50000), ((0,), 1, 50000), ((0,), 2, 1000)])
+def test_min_copies_and_truncation(engine, reads, files, m, s):
+    bufs = [reads[i] for i in files]
+    sk = engine.sketch_bytes(bufs, k=27, s=s, m=m)
+    assert_same_sketch(sk, oracle.sketch(bufs, 27, s, m))
+
+
+@pytest.mark.parametrize("chunk", [1, 7, 333, 4097, 8192, 65536, 1 << 20])
+def test_feed_chunking_is_invisible(engine, reads, chunk):
+    if chunk < 300:
+        bufs = [reads[0][:30000]]
+    else:
+        bufs = reads
+    sk = engine.sketch_bytes(bufs, k=27, s=1000, m=2, chunk=chunk)
+    assert_same_sketch(sk, oracle.sketch(bufs, 27, 1000, 2))
+
+
+@pytest.mark.parametrize("k", list(range(1, 33)))
+def test_every_k(engine, k):
+    fa = oracle.read_maybe_gz(D + "NC_001604.1.fasta.gz")
+    sk = engine.sketch_bytes([fa], k=k, s=2000, m=1, mode=AC_MODE_FASTA)
+    ref = oracle.sketch([fa], k, 2000, 1)
+    assert_same_sketch(sk, ref)
+    assert sk.info["hash_bits"] == (64 if k > 16 else 32)
+
+
+# ------------------------------------------------------------------ edge cases of the parser
+def _fasta(records, width=60, crlf=False):
+    nl = b"\r\n" if crlf else b"\n"
+    out = []
+    for name, seq in records:
+        out.append(b">" + name + nl)
+        for i in range(0, len(seq), width):
+            out.append(seq[i:i + width] + nl)
+    return b"".join(out)
+
+
+def _rand_seq(rng, n, alphabet=b"ACGT", p=None):
+    return rng.choice(list(alphabet), size=n, p=p).astype(np.uint8).tobytes()
+
+
+def test_fasta_multirecord_n_lowercase_short_records(engine):
+    rng = np.random.default_rng(11)
+    recs = [(b"r%d desc" % i, _rand_seq(rng, int(n), b"ACGTacgtNn", [.23, .23, .23, .23, .02, .02, .01, .01, .01, .01]))
+            for i, n in enumerate([5000, 26, 27, 28, 0, 1, 70000, 59, 60, 61, 12345])]
+    for width in (60, 80, 1, 7, 100000):
+        fa = _fasta(recs, width)
+        for k, s in ((27, 500), (16, 300)):
+            sk = engine.sketch_bytes([fa], k=k, s=s, m=1, mode=AC_MODE_FASTA)
+            assert_same_sketch(sk, oracle.sketch([fa], k, s, 1))
+
+
+def test_fasta_crlf_and_no_trailing_newline_and_blank_tail(engine):
+    rng = np.random.default_rng(12)
+    recs = [(b"a", _rand_seq(rng, 3000)), (b"b", _rand_seq(rng, 2000))]
+    base = _fasta(recs, 70)
+    for fa in (base.rstrip(b"\n"), base + b"\n\n\n", b"\n\n" + base, _fasta(recs, 70, crlf=True)):
+        sk = engine.sketch_bytes([fa], k=21, s=400, m=1, mode=AC_MODE_FASTA)
+        assert_same_sketch(sk, oracle.sketch([fa], 21, 400, 1))
+
+
+def test_single_line_fasta_spanning_many_tiles(engine):
+    rng = np.random.default_rng(13)
+    fa = b">one\n" + _rand_seq(rng, 300000) + b"\n>two\n" + _rand_seq(rng, 100) + b"\n"
+    sk = engine.sketch_bytes([fa], k=27, s=5000, m=1, mode=AC_MODE_FASTA, chunk=50001)
+    assert_same_sketch(sk, oracle.sketch([fa], 27, 5000, 1))
+
+
+def _fastq(rng, n, lens=(150,), n_rate=0.01, crlf=False, qual_at=False):
+    nl = b"\r\n" if crlf else b"\n"
+    out = []
+    for i in range(n):
+        L = int(rng.choice(lens))
+        seq = _rand_seq(rng, L, b"ACGTN", [(1 - n_rate) / 4] * 4 + [n_rate])
+        qual = bytes(rng.integers(33, 74, L, dtype=np.uint8))
+        if qual_at and L:
+            qual = b"@" + qual[1:] if i % 3 == 0 else b"+" + qual[1:]
+        out.append(b"@r%d x\n"[:-1] % i + nl + seq + nl + b"+" + nl + qual + nl)
+    return b"".join(out)
+
+
+def test_fastq_ragged_reads_short_reads_and_tricky_quality(engine):
+    rng = np.random.default_rng(14)
+    g = _rand_seq(rng, 4000)
+
+    def reads_from_genome(n, lens):
+        out = []
+        for i in range(n):
+            L = int(rng.choice(lens))
+            st = int(rng.integers(0, len(g) - L + 1))
+            q = bytes(rng.integers(33, 74, L, dtype=np.uint8))
+            if L:
+                q = (b"@" if i % 2 else b"+") + q[1:]  # quality lines that look like headers / separators
+            out.append(b"@r%d\n" % i + g[st:st + L] + b"\n+r%d\n" % i + q + b"\n")
+        return b"".join(out)
+
+    fq = reads_from_genome(3000, (150, 151, 26, 27, 28, 1, 0, 75, 250))
+    for m in (1, 2, 3):
+        sk = engine.sketch_bytes([fq], k=27, s=1000, m=m)
+        assert_same_sketch(sk, oracle.sketch([fq], 27, 1000, m))
+    fq2 = _fastq(rng, 500, crlf=True)
+    sk = engine.sketch_bytes([fq2, fq], k=27, s=1000, m=1)
+    assert_same_sketch(sk, oracle.sketch([fq2, fq], 27, 1000, 1))
+    # no trailing newline
+    sk = engine.sketch_bytes([fq.rstrip(b"\n")], k=27, s=1000, m=2, chunk=9999)
+    assert_same_sketch(sk, oracle.sketch([fq.rstrip(b"\n")], 27, 1000, 2))
+
+
+def test_reads_mode_merges_fasta_and_fastq_files(engine, reads):
+    fa = oracle.read_maybe_gz(D + "NC_001416.1.fasta.gz")
+    bufs = [reads[0][:400000], fa, reads[1][:200000]]
+    # cut at record boundaries so the FASTQ pieces stay well-formed
+    bufs[0] = bufs[0][:bufs[0].rfind(b"\n@") + 1]
+    bufs[2] = bufs[2][:bufs[2].rfind(b"\n@") + 1]
+    sk = engine.sketch_bytes(bufs, k=27, s=3000, m=2)
+    assert_same_sketch(sk, oracle.sketch(bufs, 27, 3000, 2))
+
+
+def test_multiline_fastq_is_rejected_loudly(engine):
+    fq = b"@r1\nACGTACGTACGTACGTACGTACGTACGTACGT\nACGTACGTACGTACGTACGTACGTACGTACGT\n+\n" + b"I" * 32 + b"\n" + b"I" * 32 + b"\n"
+    with pytest.raises(_lib.AcError) as e:
+        engine.sketch_bytes([fq], k=27, s=100, m=1)
+    assert e.value.code == _lib.AC_E_FORMAT
+    with pytest.raises(_lib.AcError):  # truncated record
+        engine.sketch_bytes([b"@r1\nACGTACGTACGTACGTACGTACGTACGTACGT\n+\n"], k=27, s=100, m=1)
+
+
+def test_all_records_shorter_than_k(engine):
+    with pytest.raises(_lib.NoRecordsError):
+        engine.sketch_bytes([b">a\nACGTACGT\n>b\nACGT\n"], k=27, s=100, m=1, mode=AC_MODE_FASTA)
+    with pytest.raises(_lib.NoRecordsError):  # nothing reaches min-copies 3
+        engine.sketch_bytes([b"@a\n" + b"ACGTTGCAAGGCTTAACCGGTTAGCATCGATCG" + b"\n+\n" + b"I" * 33 + b"\n"], k=27, s=100, m=3)
+
+
+# ------------------------------------------------------------------ big inputs: segments, speculation, shrinking threshold
+def test_multi_segment_reads_speculative_threshold(engine):
+    """~110 MB of reads from a 2 Mb genome: several 32 MiB segments, tau starts at 1/16 of the hash
+    space and shrinks; the oracle (all cores) must agree bit for bit."""
+    contigs = synth.genome(seed=99, scale=2.0 / 12.4)
+    fq = synth.fastq_reads(contigs, 340_000, seed=100)
+    buf = fq.tobytes()
+    assert len(buf) > 3 * (32 << 20)
+    ref = oracle.sketch_parallel([buf], 27, 50000, 3)
+    sk = engine.sketch_bytes([buf], k=27, s=50000, m=3, chunk=16 << 20)
+    assert_same_sketch(sk, ref)
+    assert sk.info["passes"] == 1 and sk.info["final_tau"] < (1 << 60)
+    assert sk.info["n_candidates"] < sk.info["n_kmers"] // 8
+    # device-resident feed (what bench.py's `value` times) gives the same sketch
+    import torch
+    t = torch.frombuffer(bytearray(buf), dtype=torch.uint8).cuda()
+    import ctypes as C
+    job = engine._begin(27, 50000, 42, 3, AC_MODE_READS)
+    _lib.check(engine.lib.ac_sketch_feed_device(job, t.data_ptr(), t.numel(), 0, 1))
+    from auriclass_b200.mash_gpu import StreamStats
+    sk2 = engine._end(job, "dev", 27, 50000, StreamStats())
+    assert_same_sketch(sk2, ref)
+
+
+def test_speculation_failure_falls_back_exactly(engine):
+    """Small genome, many reads: fewer than s qualified hashes exist below the speculative
+    threshold, so the pass is repeated over the retained input with tau = max."""
+    rng = np.random.default_rng(5)
+    contigs = [np.frombuffer(_rand_seq(rng, 30000), np.uint8)]
+    fq = synth.fastq_reads(contigs, 140_000, seed=6).tobytes()  # ~45 MB > one segment
+    ref = oracle.sketch_parallel([fq], 27, 50000, 3)
+    sk = engine.sketch_bytes([fq], k=27, s=50000, m=3, chunk=8 << 20)
+    assert_same_sketch(sk, ref)
+    assert sk.info["passes"] == 2
+
+
+def test_fasta_genome_scale(engine):
+    contigs = synth.genome(seed=3, scale=0.25)
+    fa = synth.fasta_bytes(contigs)
+    sk = engine.sketch_bytes([fa], k=27, s=50000, m=1, mode=AC_MODE_FASTA)
+    assert_same_sketch(sk, oracle.sketch([fa], 27, 50000, 1))
+
+
+def test_sharding_invariance_property(engine, reads):
+    """Order independence: any permutation / split of the read files gives the same sketch."""
+    a = engine.sketch_bytes([reads[0], reads[1]], k=27, s=1000, m=3)
+    b = engine.sketch_bytes([reads[1], reads[0]], k=27, s=1000, m=3)
+    ha, ca = a.hashes()
+    hb, cb = b.hashes()
+    assert np.array_equal(ha, hb) and np.array_equal(ca, cb)
+
+
+# ------------------------------------------------------------------ distance / p-value
+def test_dist_matches_oracle_including_pvalues(engine):
+    rng = np.random.default_rng(21)
+    base = np.unique(rng.integers(0, 1 << 62, 70000, dtype=np.uint64))
+    refs, lens = [], []
+    for i, (n, keep) in enumerate([(50000, 1.0), (50000, 0.9), (30000, 0.5), (50000, 0.001), (10, 1.0), (50000, 0.0)]):
+        mask = rng.random(base.size) < keep
+        own = np.unique(rng.integers(0, 1 << 62, 70000, dtype=np.uint64))
+        h = np.sort(np.concatenate([base[mask], own[: base.size - int(mask.sum())]]))[:n]
+        refs.append(np.unique(h))
+        lens.append(int(rng.integers(1000, 20_000_000)))
+    from auriclass_b200.msh import MshReference, MshSketch
+    for k in (27, 16, 21):
+        m = MshSketch(kmer_size=k, sketch_size=50000, hash_bits=64 if k > 16 else 32,
+                      references=[MshReference("r%d" % i, "", lens[i], refs[i] if k > 16 else np.unique(refs[i] & np.uint64(0xFFFFFFFF)))
+                                  for i in range(len(refs))])
+        gr = engine.load_references(m)
+        for qi in (0, 1, 3, 4):
+            qh = m.references[qi].hashes
+            qlen = 12_400_000 if k > 16 else 48502
+            q = engine.sketch_from_hashes(qh, k, 50000, qlen)
+            rows = engine.dist(gr, q)
+            for r, ref in zip(rows, m.references):
+                d, p, c, n = oracle.dist(ref.hashes, qh, 50000, k, ref.length, qlen)
+                assert (r.common, r.denom) == (c, n)
+                assert rel_close(r.distance, d), (r.distance, d)
+                assert rel_close(r.pvalue, p, 1e-9) or abs(r.pvalue - p) < 1e-300, (r.pvalue, p)
+        gr.free()
+
+
+def test_dist_small_s_cap(engine, ref_msh):
+    lam, t7 = ref_msh.references
+    from auriclass_b200.msh import MshSketch
+    m = MshSketch(kmer_size=27, sketch_size=1000, references=[lam, t7])
+    m.references = [type(lam)(lam.name, "", lam.length, lam.hashes[:1000]), type(t7)(t7.name, "", t7.length, t7.hashes[:1000])]
+    gr = engine.load_references(m)
+    q = engine.sketch_from_hashes(lam.hashes[:1000], 27, 1000, lam.length)
+    rows = engine.dist(gr, q)
+    for r, ref in zip(rows, m.references):
+        d, p, c, n = oracle.dist(ref.hashes, lam.hashes[:1000], 1000, 27, ref.length, lam.length)
+        assert (r.common, r.denom) == (c, n) and rel_close(r.distance, d)
+
+
+def test_k_mismatch_is_an_error(engine, ref_msh):
+    q = engine.sketch_from_hashes(ref_msh.references[0].hashes, 21, 50000, 48502)
+    with pytest.raises(_lib.AcError) as e:
+        engine.dist(engine.load_references(D + "ref_sketch.msh"), q)
+    assert e.value.code == _lib.AC_E_PARAM_MISMATCH
+
+
+def test_launch_counter_counts_our_kernels(engine, reads):
+    n0 = engine.launch_count()
+    engine.sketch_bytes([reads[0]], k=27, s=1000, m=1)
+    assert engine.launch_count() - n0 >= 5
