@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_fq_pass_c(SegDesc sd, const Til
                                                            JobDev *__restrict__ jd, uint8_t *__restrict__ Z) {
     __shared__ uint32_t s_w[33];
     __shared__ uint32_t s_last[8];
-    __shared__ uint32_t s_words[K1_THREADS * 8];
+    __shared__ __align__(16) uint32_t s_words[K1_THREADS * 8];
     const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TileIn ti = tin[tile];
     uint32_t w[8];
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_fa_pass_c(SegDesc sd, const Til
                                                            JobDev *__restrict__ jd, uint8_t *__restrict__ Z) {
     __shared__ uint32_t s_w[33];
     __shared__ uint32_t s_last[8];
-    __shared__ uint32_t s_words[K1_THREADS * 8];
+    __shared__ __align__(16) uint32_t s_words[K1_THREADS * 8];
     const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TileIn ti = tin[tile];
     uint32_t w[8];

@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py -- FASTQ Gbases/s sketched with the -m filter (BASELINE.json metric) on N B200s.
+
+A step = one pass of the hot path (parse -> canonical k-mer MurmurHash3 -> exact min-copies
+count -> bottom-s -> estimates) over one isolate's reads.  Workload at N=1 = BASELINE configs[1]:
+a single R1 file of 150 bp synthetic reads at ~50x of a 12.4 Mb genome (4,133,334 reads,
+620 Mbp, 1.33 GB of 4-line FASTQ text), k=27 s=50000 m=3.  For N>1 every rank sketches its own
+C2-sized shard of the same isolate (weak scaling) and the ranks merge by hash range over NCCL.
+
+  value      : device-resident throughput (text already in HBM), CUDA-event time per step
+  e2e        : same metric through the public API from pinned HOST memory: H2D copies of the
+               text, sketch, dist against the 24 clade references, D2H of the rows, wall clock
+  roofline   : dominant kernel (k2_hash): algorithmic bytes / CUDA-event time vs measured HBM peak;
+               roofline_int: the binding roofline, 84 int32 instr per k-mer vs measured issue peak
+  cpu_baseline / --impl reference : the oracle (CPU restatement of Mash) on the host cores
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+K, S, M = 27, 50000, 3
+N_READS_C2 = 4_133_334
+READ_LEN = 150
+SEED_GENOME, SEED_READS = 20240001, 20240002
+I_ALG = 84  # int32 instructions per k-mer for MurmurHash3_x64_128 over 27 bytes, h1 only
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------- inputs
+def make_reads(n_reads: int, seed: int, tag: int, alloc):
+    """C2 reads as 4-line FASTQ text, generated straight into a buffer from `alloc(nbytes)`."""
+    from auriclass_b200 import synth
+    contigs = synth.genome(SEED_GENOME)
+    nbytes = n_reads * synth.record_bytes(READ_LEN, tag)
+    buf = alloc(nbytes)
+    synth.fastq_reads(contigs, n_reads, seed, READ_LEN, file_tag=tag, out=buf)
+    return buf[:nbytes], contigs
+
+
+def clade_names():
+    p = ROOT / "data" / "clade_names.txt"
+    return [l.strip() for l in p.read_text().splitlines() if l.strip()]
+
+
+def reference_genomes(contigs):
+    """24 references: 11 'auris' = G0 mutated at 0.05..1 %, 13 random outgroups."""
+    from auriclass_b200 import synth
+    out = []
+    for i in range(11):
+        rate = 0.0005 + (0.01 - 0.0005) * i / 10
+        out.append(synth.mutate(contigs, rate, 20240010 + i))
+    for i in range(13):
+        rng = np.random.Generator(np.random.PCG64(20240030 + i))
+        n = int(rng.integers(10_000_000, 16_000_000))
+        out.append([np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n, dtype=np.uint8)]])
+    return out
+
+
+def build_reference_msh(path: Path, contigs, sketch_fn):
+    from auriclass_b200 import synth
+    from auriclass_b200.msh import MshReference, MshSketch, write_msh
+    names = clade_names()
+    refs = []
+    for name, g in zip(names, reference_genomes(contigs)):
+        h, length = sketch_fn(synth.fasta_bytes(g, prefix=name))
+        refs.append(MshReference(name, "", int(length), h))
+    write_msh(path, MshSketch(kmer_size=K, sketch_size=S, references=refs))
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle)
+def cpu_sketch(buf: np.ndarray, threads: int = 0):
+    from oracle import oracle
+    return oracle.sketch_parallel([buf.tobytes() if not isinstance(buf, bytes) else buf], K, S, M, threads=threads)
+
+
+def cpu_baseline_sample(text: np.ndarray, n_reads_sample: int, rec: int) -> dict:
+    from oracle import oracle
+    sample = text[: n_reads_sample * rec].tobytes()
+    cores = oracle.num_threads()
+    t0 = time.perf_counter()
+    sk = oracle.sketch_parallel([sample], K, S, M)
+    dt = time.perf_counter() - t0
+    bases = n_reads_sample * READ_LEN
+    return {"value": bases / dt / 1e9, "unit": "Gbases/s", "cores": cores, "kind": "port",
+            "sample": f"first {n_reads_sample} reads of the workload ({bases / 1e6:.1f} Mbp, {len(sample) / 1e6:.0f} MB FASTQ), "
+                      f"oracle.sketch_parallel (restated-Mash CPU baseline, not the mash binary), {dt:.2f} s",
+            "n_hashes": int(len(sk.hashes))}
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from auriclass_b200 import synth
+    from oracle import oracle
+    rec = synth.record_bytes(READ_LEN, 0)
+    n_sample = min(args.reads, args.ref_sample_reads)
+    text, contigs = make_reads(n_sample, SEED_READS, 0, lambda n: np.empty(n, np.uint8))
+    sample = text.tobytes()
+    cores = oracle.num_threads()
+    bases = n_sample * READ_LEN
+    # 24 reference sketches (dist is part of the per-isolate path); built once, outside the timed steps
+    refs = []
+    if not args.no_dist:
+        for g in reference_genomes(contigs)[: args.n_refs]:
+            sk = oracle.sketch_parallel([synth.fasta_bytes(g)], K, S, 1)
+            refs.append((sk.hashes, sk.total_len))
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        sk = oracle.sketch_parallel([sample], K, S, M)
+        for h, length in refs:
+            oracle.dist(h, sk.hashes, S, K, length, int(sk.genome_size))
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = bases / (ms * 1e-3) / 1e9
+    desc = (f"{n_sample} reads x {READ_LEN} bp ({bases / 1e6:.1f} Mbp, {len(sample) / 1e6:.0f} MB FASTQ) per step: bounded sample of the "
+            f"C2 workload; oracle.sketch_parallel + {len(refs)} oracle.dist on {cores} host threads "
+            "(restated-Mash CPU implementation; the mash binary is not available)")
+    print(json.dumps({
+        "impl": "reference", "metric": "FASTQ Gbases/s sketched (-m filter)", "value": val, "unit": "Gbases/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "C2: auriclass FASTQ mode, single R1 file, 150 bp synthetic reads at ~50x of a 12.4 Mb genome, "
+                               "k=27 s=50000 m=3 (bounded sample per step)", "sample": desc},
+        "cpu_baseline": {"value": val, "unit": "Gbases/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=N_READS_C2, help="reads per rank (default: the C2 workload)")
+    ap.add_argument("--ref-sample-reads", type=int, default=400_000)
+    ap.add_argument("--cpu-sample-reads", type=int, default=400_000)
+    ap.add_argument("--n-refs", type=int, default=24)
+    ap.add_argument("--no-dist", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--feed-chunk-mb", type=int, default=32)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        log("note: timing rules ask for >= 3 warm-up steps")
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: auriclass_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from auriclass_b200 import _lib, synth
+    from auriclass_b200._lib import AC_MODE_READS, SketchInfo, check
+    from auriclass_b200.mash_gpu import GpuSketch, MashGPU, StreamStats
+
+    eng = MashGPU(local)
+    lib = eng.lib
+    rec = synth.record_bytes(READ_LEN, 0)
+
+    # ---- inputs: this rank's shard, generated into pinned host memory, then one resident device copy
+    t0 = time.perf_counter()
+    nbytes = args.reads * rec
+    pinned_ptr = lib.ac_alloc_pinned(nbytes)
+    if not pinned_ptr:
+        raise MemoryError("ac_alloc_pinned failed")
+    host = np.ctypeslib.as_array((C.c_ubyte * nbytes).from_address(pinned_ptr))
+    text, contigs = make_reads(args.reads, SEED_READS + 1000 * rank, 0, lambda n: host)
+    dev_text = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    dev_text.copy_(torch.from_numpy(text), non_blocking=False)
+    torch.cuda.synchronize()
+    log(f"[rank {rank}] generated {args.reads} reads ({nbytes / 1e9:.3f} GB FASTQ) in {time.perf_counter() - t0:.1f} s")
+    bases_per_rank = args.reads * READ_LEN
+
+    # ---- 24 clade references: sketched by the library itself, written as .msh, read back by the host reader
+    refs = None
+    if not args.no_dist:
+        t0 = time.perf_counter()
+        tmp = Path(tempfile.mkdtemp()) / "synthetic_clade_references.msh"
+
+        def gpu_fasta_sketch(fa: bytes):
+            sk = eng.sketch_bytes([fa], k=K, s=S, m=1, mode=_lib.AC_MODE_FASTA)
+            h, _ = sk.hashes()
+            length = sk.length
+            sk.free()
+            return h, length
+        from auriclass_b200 import synth as _s  # noqa: F401
+        names = clade_names()[: args.n_refs]
+        from auriclass_b200.msh import MshReference, MshSketch, write_msh
+        rl = []
+        for name, g in zip(names, reference_genomes(contigs)):
+            h, length = gpu_fasta_sketch(synth.fasta_bytes(g, prefix=name))
+            rl.append(MshReference(name, "", int(length), h))
+        write_msh(tmp, MshSketch(kmer_size=K, sketch_size=S, references=rl))
+        refs = eng.load_references(tmp)
+        log(f"[rank {rank}] built {len(rl)} reference sketches in {time.perf_counter() - t0:.1f} s")
+
+    if world > 1:
+        from auriclass_b200.sharded import ShardedSketcher
+        sharded = ShardedSketcher(eng, rank, world)
+
+    def step_device():
+        """hot path with the text resident in HBM (what `value` times)"""
+        job = eng._begin(K, S, 42, M, AC_MODE_READS)
+        check(lib.ac_sketch_feed_device(job, dev_text.data_ptr(), nbytes, 0, 1))
+        if world > 1:
+            return sharded.finish(job, K, S, M)
+        return eng._end(job, "reads_R1.fq", K, S, StreamStats())
+
+    chunk = args.feed_chunk_mb << 20
+
+    def step_e2e():
+        """public API from pinned host memory: H2D of the text every step, dist, rows back on the host"""
+        job = eng._begin(K, S, 42, M, AC_MODE_READS)
+        off = 0
+        while off < nbytes:
+            n = min(chunk, nbytes - off)
+            check(lib.ac_sketch_feed(job, pinned_ptr + off, n, 0, 1 if off + n >= nbytes else 0))
+            off += n
+        if world > 1:
+            sk = sharded.finish(job, K, S, M)
+        else:
+            sk = eng._end(job, "reads_R1.fq", K, S, StreamStats())
+        rows = eng.dist(refs, sk) if refs is not None else []
+        return sk, rows
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        check(lib.ac_sync(eng.ctx))
+
+    # ---- warm-up
+    sk = None
+    for _ in range(args.warmup):
+        sk = step_device()
+        sk.free()
+    # ---- timed: device-resident
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = eng.launch_count()
+    dev_ms, t0 = [], time.perf_counter()
+    for _ in range(args.steps):
+        sk = step_device()
+        dev_ms.append(eng.last_job_times()["total_ms"])
+        info = dict(sk.info)
+        sk.free()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    launches = eng.launch_count() - l0
+    # ---- timed: end to end from pinned host memory
+    for _ in range(2):
+        s_, _r = step_e2e()
+        s_.free()
+    barrier()
+    t0 = time.perf_counter()
+    rows = []
+    for _ in range(args.steps):
+        s_, rows = step_e2e()
+        s_.free()
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+
+    # ---- kernel breakdown of one more (profiled) step; integer peak
+    eng.set_profile(True)
+    sk = step_device()
+    prof = eng.last_job_times()
+    n_kmers, n_cand, passes = sk.info["n_kmers"], sk.info["n_candidates"], sk.info["passes"]
+    n_hashes = len(sk)
+    sk.free()
+    eng.set_profile(False)
+    int_peak = eng.int_peak()
+
+    # max over ranks
+    ms_step = float(np.mean(dev_ms)) if world == 1 else wall_ms
+    if world > 1:
+        t = torch.tensor([ms_step, wall_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, wall_ms, e2e_ms = [float(x) for x in t.tolist()]
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        n_rec = args.reads
+        # K2 algorithmic bytes per step: the base stream (1 B per base + 1 separator per read) in, 8 B per candidate out
+        k2_bytes = bases_per_rank + n_rec + 8 * n_cand
+        hash_s = prof["hash_ms"] * 1e-3
+        n_seg = -(-nbytes // (32 << 20))
+        traffic = None
+        tp = ROOT / "profiles" / "k2_traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        out = {
+            "metric": "FASTQ Gbases/s sketched (-m filter)",
+            "value": world * bases_per_rank / (ms_step * 1e-3) / 1e9,
+            "unit": "Gbases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "wall_ms_per_step": wall_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {
+                "workload": ("C2: auriclass FASTQ mode, single R1 file, 150 bp synthetic reads at ~50x of a 12.4 Mb genome "
+                             f"({args.reads} reads, {bases_per_rank / 1e6:.1f} Mbp, {nbytes / 1e9:.3f} GB 4-line FASTQ per GPU), "
+                             "k=27 s=50000 m=3 seed 42"),
+                "l2": "inputs larger than L2 (1.33 GB text per step vs 126 MB)",
+                "timing": "value: CUDA events on the library's compute stream, first to last kernel of each job; "
+                          "wall_ms_per_step brackets the same steps with synchronize on both sides",
+                "parallelism": "1 GPU" if world == 1 else f"read-block sharded over {world} GPUs, hash-range all-to-all + all-gather (NCCL)",
+                "n_kmers_per_gpu": int(n_kmers), "n_candidates_per_gpu": int(n_cand), "sketch_hashes": int(n_hashes),
+                "passes": int(passes),
+            },
+            "e2e": {"value": world * bases_per_rank / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s",
+                    "ms_per_step": e2e_ms, "wall_s_per_isolate": e2e_ms * 1e-3,
+                    "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(len(rows) * 32 + 8 * 256),
+                    "includes": "H2D of the FASTQ text from pinned memory in 32 MB feeds, sketch, dist vs "
+                                f"{len(rows)} references, D2H of the rows; gzip inflate not included (timed separately by the host streamer)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": k2_bytes / hash_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": k2_bytes / hash_s / 1e9 / hbm_peak, "traffic": traffic,
+                         "kernel": "k2_hash<27>", "launches_per_step": int(n_seg), "avg_launch_ms": prof["hash_ms"] / n_seg,
+                         "algorithmic_bytes_per_launch": k2_bytes / n_seg, "peak_source": peak_src,
+                         "note": "K2 is integer-issue bound, not HBM bound: see roofline_int"},
+            "roofline_int": {"bound": "int32-issue", "achieved": n_kmers * I_ALG / hash_s / 1e12, "peak": int_peak / 1e12,
+                             "unit": "Tinstr/s", "frac": n_kmers * I_ALG / hash_s / int_peak,
+                             "instr_per_kmer": I_ALG, "peak_source": "ac_int_peak: IMAD+LOP3 microbenchmark run in this process"},
+            "kernel_ms": {"parse_k1": prof["parse_ms"], "hash_k2": prof["hash_ms"], "select_k3_k4": prof["select_ms"],
+                          "job_total": prof["total_ms"]},
+        }
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_sample(text, min(args.reads, args.cpu_sample_reads), rec)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+    lib.ac_free_pinned(pinned_ptr)
+
+
+if __name__ == "__main__":
+    main()
