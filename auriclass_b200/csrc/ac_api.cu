@@ -55,6 +55,7 @@ struct ac_ctx {
     float last_ms[4];
     bool profile;
     size_t cand_cap;           // entries in the candidate / sort buffers
+    size_t seg_bytes;          // raw text per segment (SEG_BYTES, or AC_SEG_MB for tests)
     SelectBufs sb;
     bool sb_ok;
     uint8_t *d_Z;
@@ -207,10 +208,14 @@ extern "C" int ac_create(int device, ac_ctx **out) {
     const char *cap_env = getenv("AC_CAND_CAP");
     c->cand_cap = cap_env ? (size_t)strtoull(cap_env, nullptr, 10) : ((size_t)48 << 20);
     if (c->cand_cap < (1u << 16)) c->cand_cap = 1u << 16;
+    const char *seg_env = getenv("AC_SEG_MB");
+    c->seg_bytes = seg_env ? ((size_t)strtoull(seg_env, nullptr, 10) << 20) : SEG_BYTES;
+    if (c->seg_bytes < ((size_t)1 << 20)) c->seg_bytes = (size_t)1 << 20;
+    if (c->seg_bytes > ((size_t)1 << 30)) c->seg_bytes = (size_t)1 << 30;
     CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
-    CK(cudaMalloc(&c->d_Z, Z_CARRY + SEG_BYTES + K2_TILE + 4096));
-    const size_t max_tiles = SEG_BYTES / K1_TILE + 4;
+    CK(cudaMalloc(&c->d_Z, Z_CARRY + c->seg_bytes + K2_TILE + 4096));
+    const size_t max_tiles = c->seg_bytes / K1_TILE + 4;
     CK(cudaMalloc(&c->d_sums, max_tiles * sizeof(TileSum)));
     CK(cudaMalloc(&c->d_tin, max_tiles * sizeof(TileIn)));
     CK(cudaMalloc(&c->d_jd, sizeof(JobDev)));
@@ -382,7 +387,7 @@ static int start_pass(ac_job *j, unsigned long long tau0, bool safe) {
     CK(cudaStreamSynchronize(c->s_comp));
     j->pass_started = true; j->tau0 = tau0; j->safe = safe; j->passes++;
     j->proc_piece = 0; j->proc_off = 0; j->first_of_stream = true;
-    j->cand_bound = 0; j->n_table_host = 0; j->tau_host = tau0; j->bytes_done = 0; j->next_mark = 2 * SEG_BYTES;
+    j->cand_bound = 0; j->n_table_host = 0; j->tau_host = tau0; j->bytes_done = 0; j->next_mark = c->seg_bytes;
     if (j->passes == 1) CK(cudaEventRecord(c->ev_job0, c->s_comp));
     return AC_OK;
 }
@@ -442,19 +447,19 @@ static int pump(ac_job *j, bool all) {
         const size_t avail = p.len - j->proc_off;
         const size_t usable = open ? (avail > HOLD_BACK ? avail - HOLD_BACK : 0) : avail;
         if (open && usable == 0) break;
-        const size_t len = std::min(usable, SEG_BYTES);
-        const bool seg_last = p.last_of_file && (j->proc_off + len == p.len);
         if (!all) {
-            if (j->pending < SEG_BYTES + HOLD_BACK) break;
-            if (open && len < SEG_BYTES) break;
+            if (j->pending < j->ctx->seg_bytes + HOLD_BACK) break;
+            if (open && usable < j->ctx->seg_bytes) break;
         }
         if (!j->pass_started) {
             // the size fed so far decides the speculative threshold: big inputs start at 1/16 of
             // the hash space, small ones keep everything (tau = max, nothing to verify)
-            const bool big = j->pending >= SEG_BYTES;
+            const bool big = j->pending >= std::min(SEG_SAFE_BYTES, j->ctx->seg_bytes);
             int rc = start_pass(j, big ? (space_max(j) >> 4) : space_max(j), !big);
             if (rc) return rc;
         }
+        const size_t len = std::min(usable, j->safe ? std::min(SEG_SAFE_BYTES, j->ctx->seg_bytes) : j->ctx->seg_bytes);
+        const bool seg_last = p.last_of_file && (j->proc_off + len == p.len);
         int rc = run_segment(j, j->proc_piece, j->proc_off, len, seg_last);
         if (rc) return rc;
         j->pending -= std::min(j->pending, len);

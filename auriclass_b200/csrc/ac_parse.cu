@@ -32,8 +32,16 @@ __device__ __forceinline__ uint32_t bit_range(int a, int b) {  // bits [a, b), 0
 }
 
 struct ChunkMasks {
-    uint32_t valid, nl, at, gt, plus;
+    uint32_t valid, nl;
+    const uint8_t *bytes;  // address of the chunk's byte 0 (line-start characters are read from here, L1 hits)
 };
+
+// 0x80 in every byte of w equal to '\n' (exact: no borrow artefacts)
+__device__ __forceinline__ uint32_t newline_bits(uint32_t w) {
+    const uint32_t x = w ^ 0x0A0A0A0Au;
+    const uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(t | x | 0x7F7F7F7Fu);
+}
 
 // Loads the thread's 32 raw bytes (two 16-byte vector loads) and builds per-byte masks.
 __device__ __forceinline__ void load_chunk(const SegDesc &sd, uint32_t tile, uint32_t tid, uint32_t w[8],
@@ -56,15 +64,11 @@ __device__ __forceinline__ void load_chunk(const SegDesc &sd, uint32_t tile, uin
         for (int jj = 0; jj < 8; jj++)
             if (jj == (j >> 2)) w[jj] = (w[jj] & ~(0xFFu << (8 * (j & 3)))) | (0x0Au << (8 * (j & 3)));
     }
-    uint32_t nl = 0, at = 0, gt = 0, pl = 0;
+    uint32_t nl = 0;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        nl |= gather_nib(__vcmpeq4(w[j], 0x0A0A0A0Au)) << (4 * j);
-        at |= gather_nib(__vcmpeq4(w[j], 0x40404040u)) << (4 * j);
-        gt |= gather_nib(__vcmpeq4(w[j], 0x3E3E3E3Eu)) << (4 * j);
-        pl |= gather_nib(__vcmpeq4(w[j], 0x2B2B2B2Bu)) << (4 * j);
-    }
-    m.nl = nl & m.valid; m.at = at & m.valid; m.gt = gt & m.valid; m.plus = pl & m.valid;
+    for (int j = 0; j < 8; j++) nl |= (((newline_bits(w[j]) >> 7) * 0x01020408u) >> 24) << (4 * j);
+    m.nl = nl & m.valid;
+    m.bytes = sd.base + pos;
 }
 
 // Is the byte just before this thread's first valid byte a newline?  (seg_first: value to use
@@ -89,11 +93,18 @@ __device__ __forceinline__ bool prev_is_newline(const SegDesc &sd, uint32_t tile
     return r;
 }
 
+// four bytes -> upper-case A/C/G/T where valid, 0x01 elsewhere.  Bits 1-2 of a base letter index
+// the table "ACTG"; a byte is valid iff the table letter equals its case-folded value.
 __device__ __forceinline__ uint32_t sanitise4(uint32_t w) {
     const uint32_t u = w & 0xDFDFDFDFu;
-    const uint32_t ok = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) |
-                        __vcmpeq4(u, 0x54545454u);
-    return (u & ok) | (~ok & 0x01010101u);
+    const uint32_t c = (w >> 1) & 0x03030303u;            // 2-bit index per byte
+    const uint32_t t = c | (c >> 4);                      // nibble pairs in bytes 0 and 2
+    const uint32_t sel = (t & 0xFFu) | ((t >> 8) & 0xFF00u);
+    const uint32_t canon = __byte_perm(0x47544341u, 0u, sel);  // table A,C,T,G
+    const uint32_t x = canon ^ u;
+    const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);  // 0x80 where valid
+    const uint32_t vm = (z >> 7) * 0xFFu;
+    return (u & vm) | (~vm & 0x01010101u);
 }
 
 // ---------------------------------------------------------------- FASTQ
@@ -172,10 +183,10 @@ __global__ void __launch_bounds__(K1_THREADS) k1_fq_pass_c(SegDesc sd, const Til
         uint32_t ph = (ti.state + L0) & 3u;
         bool ls = prev_nl;
         while (true) {
-            if (ls) {
-                const uint32_t bit = 1u << pos;
-                if (ph == 0 && !(m.at & bit)) err |= FERR_FQ_HEADER;
-                if (ph == 2 && !(m.plus & bit)) err |= FERR_FQ_PLUS;
+            if (ls && !(ph & 1u)) {
+                const uint8_t ch = __ldg(m.bytes + pos);
+                if (ph == 0 && ch != '@') err |= FERR_FQ_HEADER;
+                if (ph == 2 && ch != '+') err |= FERR_FQ_PLUS;
             }
             const uint32_t r = m.nl & (0xffffffffu << pos);
             const int end = r ? (__ffs(r) - 1) : (vhi - 1);
@@ -197,7 +208,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_fq_pass_c(SegDesc sd, const Til
         const uint32_t nib = (em >> bitoff) & 0xFu;
         if (nib) {
             const uint32_t word = s_words[warp * 256 + step * 32 + lane];
-            uint32_t sw = sanitise4(word) & ~__vcmpeq4(word, 0x0A0A0A0Au);  // newline -> record separator
+            uint32_t sw = sanitise4(word) & ~((newline_bits(word) >> 7) * 0xFFu);  // newline -> record separator
             uint32_t off = ti.out_off + e0 + __popc(em & ((1u << bitoff) - 1u));
 #pragma unroll
             for (int k = 0; k < 4; k++)
@@ -218,14 +229,14 @@ template <bool PASS_C>
 __device__ __forceinline__ FaThread fa_classify(const ChunkMasks &m, uint32_t lsm, bool known, uint32_t type) {
     FaThread o{0, 0, 0, 0, 0};
     if (!m.valid) return o;
-    const uint32_t hdr = m.at | m.gt;
     const int vlo = __ffs(m.valid) - 1, vhi = 32 - __clz(m.valid);
     int pos = vlo;
     while (true) {
         if ((lsm >> pos) & 1u) {
-            type = ((hdr >> pos) & 1u) ? 0u : 1u;
+            const uint8_t ch = __ldg(m.bytes + pos);
+            type = (ch == '>' || ch == '@') ? 0u : 1u;
             known = true;
-            if ((m.plus >> pos) & 1u) o.err |= FERR_FA_PLUS;
+            if (ch == '+') o.err |= FERR_FA_PLUS;
             if (type == 0u) { o.rest_emit += 1; if (PASS_C) { o.emit |= 1u << pos; o.sepm |= 1u << pos; } }
         }
         const uint32_t next = (pos + 1 < 32) ? (lsm & (0xffffffffu << (pos + 1))) : 0u;
@@ -257,11 +268,10 @@ __global__ void __launch_bounds__(K1_THREADS) k1_fa_pass_a(SegDesc sd, const Job
     if (tid < 3) s_acc[tid] = 0;
     const bool prev_nl = prev_is_newline(sd, tile, m, jd->at_line_start, s_last);
     const uint32_t lsm = fa_line_starts(m, prev_nl);
-    const uint32_t hdr = m.at | m.gt;
     uint32_t enc = 0;
     if (lsm) {
-        const int top = 31 - __clz(lsm);
-        enc = ((tid + 1u) << 1) | (((hdr >> top) & 1u) ? 0u : 1u);
+        const uint8_t ch = __ldg(m.bytes + (31 - __clz(lsm)));
+        enc = ((tid + 1u) << 1) | ((ch == '>' || ch == '@') ? 0u : 1u);
     }
     const uint32_t inc = block_incl_max<K1_THREADS>(enc, s_w);
     // exclusive value = inclusive value of the previous thread
@@ -309,11 +319,10 @@ __global__ void __launch_bounds__(K1_THREADS) k1_fa_pass_c(SegDesc sd, const Til
         reinterpret_cast<uint4 *>(s_words)[tid * 2 + v] = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
     const bool prev_nl = prev_is_newline(sd, tile, m, ti.first_ls, s_last);
     const uint32_t lsm = fa_line_starts(m, prev_nl);
-    const uint32_t hdr = m.at | m.gt;
     uint32_t enc = 0;
     if (lsm) {
-        const int top = 31 - __clz(lsm);
-        enc = ((tid + 1u) << 1) | (((hdr >> top) & 1u) ? 0u : 1u);
+        const uint8_t ch = __ldg(m.bytes + (31 - __clz(lsm)));
+        enc = ((tid + 1u) << 1) | ((ch == '>' || ch == '@') ? 0u : 1u);
     }
     const uint32_t inc = block_incl_max<K1_THREADS>(enc, s_w);
     uint32_t prev = __shfl_up_sync(FULL, inc, 1);

@@ -16,7 +16,7 @@ namespace {
 struct Collect {
     std::vector<uint64_t> *out;
     uint64_t base;
-    void operator()(int, uint64_t h) { out->push_back(h); }
+    void operator()(uint32_t vb, uint32_t bit, uint64_t h) { if (vb & bit) out->push_back(h); }
 };
 
 template <int K>

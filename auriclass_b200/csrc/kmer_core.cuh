@@ -41,11 +41,49 @@ AC_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
 #endif
 }
 
-AC_HD uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+// 64-bit rotate left by a compile-time amount: two funnel shifts on the device
+template <int R>
+AC_HD uint64_t rotl64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    uint32_t nlo, nhi;
+    if constexpr (R == 32) { nlo = hi; nhi = lo; }
+    else if constexpr (R < 32) { nhi = __funnelshift_l(lo, hi, R); nlo = __funnelshift_l(hi, lo, R); }
+    else { nhi = __funnelshift_l(hi, lo, R - 32); nlo = __funnelshift_l(lo, hi, R - 32); }
+    return ((uint64_t)nhi << 32) | nlo;
+#else
+    return (x << R) | (x >> (64 - R));
+#endif
+}
+
+// x * c (mod 2^64): IMAD.WIDE + 2 IMAD on the device (nvcc's own expansion spends a 4th on an add)
+AC_HD uint64_t mul64(uint64_t x, uint64_t c) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 32), cl = (uint32_t)c, ch = (uint32_t)(c >> 32);
+    uint64_t p;
+    uint32_t hi;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(xl), "r"(cl));
+    hi = (uint32_t)(p >> 32);
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(xl), "r"(ch));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(xh), "r"(cl));
+    return ((uint64_t)hi << 32) | (uint32_t)p;
+#else
+    return x * c;
+#endif
+}
+
+// keeps a value in a register: ptxas otherwise rematerialises cheap SWAR results per use
+AC_HD void pin_reg(uint32_t &v) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+r"(v));
+#else
+    (void)v;
+#endif
+}
 
 AC_HD uint64_t fmix64(uint64_t x) {
-    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
-    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33; x = mul64(x, 0xff51afd7ed558ccdULL);
+    x ^= x >> 33; x = mul64(x, 0xc4ceb9fe1a85ec53ULL);
     x ^= x >> 33;
     return x;
 }
@@ -67,27 +105,27 @@ AC_HD uint64_t murmur3_h1(const uint32_t *w, uint32_t seed) {
     if constexpr (NB >= 1) {
         uint64_t k1 = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
         uint64_t k2 = (uint64_t)w[2] | ((uint64_t)w[3] << 32);
-        k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
-        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
-        k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
-        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+        k1 = mul64(k1, c1); k1 = rotl64<31>(k1); k1 = mul64(k1, c2); h1 ^= k1;
+        h1 = rotl64<27>(h1); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+        k2 = mul64(k2, c2); k2 = rotl64<33>(k2); k2 = mul64(k2, c1); h2 ^= k2;
+        h2 = rotl64<31>(h2); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
     }
     if constexpr (NB >= 2) {
         uint64_t k1 = (uint64_t)w[4] | ((uint64_t)w[5] << 32);
         uint64_t k2 = (uint64_t)w[6] | ((uint64_t)w[7] << 32);
-        k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
-        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
-        k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
-        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+        k1 = mul64(k1, c1); k1 = rotl64<31>(k1); k1 = mul64(k1, c2); h1 ^= k1;
+        h1 = rotl64<27>(h1); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+        k2 = mul64(k2, c2); k2 = rotl64<33>(k2); k2 = mul64(k2, c1); h2 ^= k2;
+        h2 = rotl64<31>(h2); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
     }
     constexpr int T = K & 15;
     if constexpr (T > 8) {
         uint64_t k2 = (uint64_t)key_word<K, 4 * NB + 2>(w) | ((uint64_t)key_word<K, 4 * NB + 3>(w) << 32);
-        k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+        k2 = mul64(k2, c2); k2 = rotl64<33>(k2); k2 = mul64(k2, c1); h2 ^= k2;
     }
     if constexpr (T > 0) {
         uint64_t k1 = (uint64_t)key_word<K, 4 * NB>(w) | ((uint64_t)key_word<K, 4 * NB + 1>(w) << 32);
-        k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+        k1 = mul64(k1, c1); k1 = rotl64<31>(k1); k1 = mul64(k1, c2); h1 ^= k1;
     }
     h1 ^= (uint64_t)K; h2 ^= (uint64_t)K;
     h1 += h2; h2 += h1;
@@ -184,7 +222,9 @@ template <int K, int W, int I, class Emit>
 AC_HD void process_window(const uint32_t *r, const uint32_t *q, uint32_t vmask, uint32_t seed, Emit &emit) {
     if constexpr (I < W) {
         using C = RunCfg<K, W>;
-        if ((vmask >> I) & 1u) {
+        {
+            // every lane hashes every window (a warp runs the hash as soon as one lane needs it);
+            // windows touching an invalid byte are dropped at emission
             uint32_t f[C::NW], c[C::NW];
             slice_key<K, I, 0, C::NW>(r, f);
             slice_key<K, 4 * C::RW - K - I, 0, C::NW>(q, c);
@@ -192,16 +232,35 @@ AC_HD void process_window(const uint32_t *r, const uint32_t *q, uint32_t vmask, 
             uint32_t key[C::NW];
 #pragma unroll
             for (int j = 0; j < C::NW; j++) key[j] = use_rc ? c[j] : f[j];
-            emit(I, murmur3_h1<K>(key, seed));
+            emit(vmask, 1u << I, murmur3_h1<K>(key, seed));
         }
         process_window<K, W, I + 1, Emit>(r, q, vmask, seed, emit);
+    }
+}
+
+// Hash G consecutive windows.  fw: forward bytes as LE words, window i starts at byte i.
+// rw: reverse-complement bytes as LE words, window i starts at byte RC0 - i (RC0 compile time).
+// vbits: bit i = window i valid.  emit(vbits, 1<<i, h1) is called for every window.
+template <int K, int G, int RC0, int I, class Emit>
+AC_HD void process_group(const uint32_t *fw, const uint32_t *rw, uint32_t vbits, uint32_t seed, Emit &emit) {
+    if constexpr (I < G) {
+        constexpr int NW = (K + 3) / 4;
+        uint32_t f[NW], c[NW];
+        slice_key<K, I, 0, NW>(fw, f);
+        slice_key<K, RC0 - I, 0, NW>(rw, c);
+        const bool use_rc = rc_is_smaller<NW>(f, c);
+        uint32_t key[NW];
+#pragma unroll
+        for (int j = 0; j < NW; j++) key[j] = use_rc ? c[j] : f[j];
+        emit(vbits, 1u << I, murmur3_h1<K>(key, seed));
+        process_group<K, G, RC0, I + 1, Emit>(fw, rw, vbits, seed, emit);
     }
 }
 
 // Hash every valid window of one thread's run.  r[RW]: run bytes as LE words
 // (bytes past the run may hold anything; they only enter windows >= W).
 // win_ok: bit i set when window i may be emitted (range clipping by the caller).
-// emit(i, h1) is called for each surviving window; returns the window mask.
+// emit(vmask, 1<<i, h1) is called for every window (valid iff vmask & bit); returns the window mask.
 template <int K, int W, class Emit>
 AC_HD uint32_t process_run(const uint32_t *r, uint32_t win_ok, uint32_t seed, Emit &emit) {
     using C = RunCfg<K, W>;
@@ -213,7 +272,7 @@ AC_HD uint32_t process_run(const uint32_t *r, uint32_t win_ok, uint32_t seed, Em
     if (vmask == 0) return 0;
     uint32_t q[C::RW];
 #pragma unroll
-    for (int j = 0; j < C::RW; j++) q[j] = byte_perm(comp4(r[C::RW - 1 - j]), 0, 0x0123);
+    for (int j = 0; j < C::RW; j++) { q[j] = byte_perm(comp4(r[C::RW - 1 - j]), 0, 0x0123); pin_reg(q[j]); }
     process_window<K, W, 0, Emit>(r, q, vmask, seed, emit);
     return vmask;
 }

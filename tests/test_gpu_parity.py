@@ -264,6 +264,31 @@ def test_multi_segment_reads_speculative_threshold(engine):
     assert_same_sketch(sk2, ref)
 
 
+def test_many_small_segments(reads):
+    """AC_SEG_MB=1: the FASTQ fixture crosses several segment boundaries (carry of the base stream,
+    parser state, candidate consolidation between segments) and still matches the oracle."""
+    import os
+    from auriclass_b200.mash_gpu import MashGPU
+    os.environ["AC_SEG_MB"] = "1"
+    try:
+        eng = MashGPU(0)
+    finally:
+        del os.environ["AC_SEG_MB"]
+    try:
+        contigs = synth.genome(seed=7, scale=0.01)
+        fq = synth.fastq_reads(contigs, 120_000, seed=8).tobytes()  # ~38 MB: speculative, 38 segments
+        sk = eng.sketch_bytes([fq], k=27, s=2000, m=3, chunk=3 << 20)
+        assert_same_sketch(sk, oracle.sketch_parallel([fq], 27, 2000, 3))
+        assert sk.info["passes"] == 1
+        fa = synth.fasta_bytes(synth.genome(seed=9, scale=0.3))   # 3.7 MB FASTA, tau = max, 4 segments
+        sk = eng.sketch_bytes([fa], k=21, s=5000, m=1, mode=AC_MODE_FASTA, chunk=999_983)
+        assert_same_sketch(sk, oracle.sketch([fa], 21, 5000, 1))
+        sk = eng.sketch_bytes(reads, k=27, s=50000, m=3)          # 5.2 MB of reads, tau = max
+        assert_same_sketch(sk, oracle.sketch(reads, 27, 50000, 3))
+    finally:
+        eng.close()
+
+
 def test_speculation_failure_falls_back_exactly(engine):
     """Small genome, many reads: fewer than s qualified hashes exist below the speculative
     threshold, so the pass is repeated over the retained input with tau = max."""
