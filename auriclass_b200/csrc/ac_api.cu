@@ -103,7 +103,8 @@ struct ac_job {
 };
 
 struct ac_sketch {
-    ac_ctx *ctx;
+    ac_ctx *ctx;               // creator (may already be destroyed when the sketch is freed: use `dev`, not ctx->dev)
+    int dev;
     unsigned long long *d_hash;
     uint32_t *d_cnt;
     uint64_t n;
@@ -113,6 +114,7 @@ struct ac_sketch {
 
 struct ac_refs {
     ac_ctx *ctx;
+    int dev;
     unsigned long long *d_hash, *d_off, *d_len;
     int n_refs, k, s, hash_bits;
     uint64_t max_n;
@@ -189,6 +191,8 @@ static int alloc_select(ac_ctx *c, size_t sk_cap) {
     return AC_OK;
 }
 
+extern "C" void ac_sketch_abort(ac_job *j);
+
 extern "C" int ac_create(int device, ac_ctx **out) {
     if (!out) return fail(AC_E_PARAM, "ac_create: out is NULL");
     *out = nullptr;
@@ -228,6 +232,7 @@ extern "C" int ac_create(int device, ac_ctx **out) {
 extern "C" void ac_destroy(ac_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->dev);
+    if (c->active) ac_sketch_abort(c->active);  // a job cannot outlive its context
     cudaDeviceSynchronize();
     free_select(c);
     cudaFree(c->d_Z); cudaFree(c->d_sums); cudaFree(c->d_tin); cudaFree(c->d_jd); cudaFreeHost(c->h_jd);
@@ -309,6 +314,7 @@ extern "C" int ac_sketch_begin(ac_ctx *c, int k, int sketch_size, uint32_t seed,
     if (mode != AC_MODE_READS && mode != AC_MODE_FASTA) return fail(AC_E_PARAM, "unknown mode %d", mode);
     if (c->active) return fail(AC_E_STATE, "context already has an active sketch job");
     CK(cudaSetDevice(c->dev));
+    cudaGetLastError();  // a stale error of an unrelated earlier call must not be blamed on this job's launches
     {
         int rc = alloc_select(c, (size_t)sketch_size);
         if (rc) { free_select(c); return rc; }
@@ -432,7 +438,10 @@ static int run_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_o
     if (j->safe || j->bytes_done >= j->next_mark) {
         int rc = consolidate(j);
         if (rc) return rc;
-        while (j->next_mark <= j->bytes_done) j->next_mark *= 2;
+        // one early consolidation pulls tau from the speculative 1/16 down to ~1.3x its final value; after that
+        // the candidate stream is a trickle (~0.5 % of the k-mers) that is folded in when the buffer fills
+        // (cand_bound guard above) or at the end of the job
+        j->next_mark = (size_t)-1;
     }
     return AC_OK;
 }
@@ -673,7 +682,7 @@ static int finish_local(ac_job *j) {
 static int make_sketch(ac_ctx *c, const unsigned long long *d_hash, const uint32_t *d_cnt, uint64_t n, int k, int s,
                        int hash_bits, uint64_t length, ac_sketch **out) {
     ac_sketch *sk = new ac_sketch();
-    sk->ctx = c; sk->n = n; sk->k = k; sk->s = s; sk->hash_bits = hash_bits; sk->length = length;
+    sk->ctx = c; sk->dev = c->dev; sk->n = n; sk->k = k; sk->s = s; sk->hash_bits = hash_bits; sk->length = length;
     sk->d_hash = nullptr; sk->d_cnt = nullptr;
     cudaError_t e = cudaMalloc(&sk->d_hash, (n ? n : 1) * 8);
     if (e == cudaSuccess) e = cudaMalloc(&sk->d_cnt, (n ? n : 1) * 4);
@@ -738,23 +747,24 @@ extern "C" int ac_sketch_end_local(ac_job *j, uint64_t *n_entries, uint64_t *tau
 }
 
 extern "C" int ac_job_table_ranges(ac_job *j, uint64_t tau_cut, int n_ranges, uint64_t *range_begin) {
-    if (!j || !range_begin || n_ranges < 1) return fail(AC_E_PARAM, "ac_job_table_ranges: bad argument");
+    if (!j || !range_begin || n_ranges < 1 || n_ranges > MAX_RANGES) return fail(AC_E_PARAM, "ac_job_table_ranges: bad argument (1..%d ranges)", MAX_RANGES);
     if (!j->ended_local) return fail(AC_E_STATE, "call ac_sketch_end_local first");
     ac_ctx *c = j->ctx;
     CK(cudaSetDevice(c->dev));
-    const uint32_t n = c->h_jd->n_table;
-    std::vector<unsigned long long> h(n);
-    if (n) CK(cudaMemcpy(h.data(), c->sb.tab_hash, (size_t)n * 8, cudaMemcpyDeviceToHost));
     // owner of hash x = floor(x * P / (tau_cut + 1)); boundaries b_r = ceil(r * (tau_cut + 1) / P)
+    RangeBounds rb;
+    memset(&rb, 0, sizeof(rb));
+    rb.n = n_ranges; rb.tau_cut = tau_cut;
     const unsigned __int128 span = (unsigned __int128)tau_cut + 1;
-    for (int r = 0; r <= n_ranges; r++) {
-        if (r == n_ranges) {
-            range_begin[r] = std::upper_bound(h.begin(), h.end(), (unsigned long long)tau_cut) - h.begin();
-        } else {
-            const unsigned __int128 b = (span * (unsigned)r + (unsigned)n_ranges - 1) / (unsigned)n_ranges;
-            range_begin[r] = std::lower_bound(h.begin(), h.end(), (unsigned long long)b) - h.begin();
-        }
-    }
+    for (int r = 0; r < n_ranges; r++)
+        rb.b[r] = (unsigned long long)((span * (unsigned)r + (unsigned)n_ranges - 1) / (unsigned)n_ranges);
+    LaunchCtx lc{c->s_comp, &c->launches};
+    // the sort scratch is idle once the local pass has ended: its head receives the n_ranges+1 entry indices
+    unsigned long long *d_out = c->sb.keys_b;
+    launch_table_ranges(lc, c->sb, c->h_jd->n_table, rb, d_out);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(range_begin, d_out, (size_t)(n_ranges + 1) * 8, cudaMemcpyDeviceToHost, c->s_comp));
+    CK(cudaStreamSynchronize(c->s_comp));
     return AC_OK;
 }
 
@@ -838,7 +848,7 @@ extern "C" int ac_sketch_from_hashes(ac_ctx *c, const uint64_t *hashes, uint64_t
     if (k < 1 || k > 32) return fail(AC_E_PARAM, "k = %d outside 1..32", k);
     CK(cudaSetDevice(c->dev));
     ac_sketch *sk = new ac_sketch();
-    sk->ctx = c; sk->n = n; sk->k = k; sk->s = sketch_size; sk->hash_bits = k > 16 ? 64 : 32; sk->length = length;
+    sk->ctx = c; sk->dev = c->dev; sk->n = n; sk->k = k; sk->s = sketch_size; sk->hash_bits = k > 16 ? 64 : 32; sk->length = length;
     sk->d_hash = nullptr; sk->d_cnt = nullptr;
     cudaError_t e = cudaMalloc(&sk->d_hash, (n ? n : 1) * 8);
     if (e == cudaSuccess) e = cudaMalloc(&sk->d_cnt, (n ? n : 1) * 4);
@@ -852,14 +862,14 @@ extern "C" uint64_t ac_sketch_size(const ac_sketch *sk) { return sk ? sk->n : 0;
 extern "C" uint64_t ac_sketch_length(const ac_sketch *sk) { return sk ? sk->length : 0; }
 extern "C" int ac_sketch_hashes(const ac_sketch *sk, uint64_t *hashes, uint32_t *counts) {
     if (!sk) return fail(AC_E_PARAM, "sketch is NULL");
-    CK(cudaSetDevice(sk->ctx->dev));
+    CK(cudaSetDevice(sk->dev));
     if (sk->n && hashes) CK(cudaMemcpy(hashes, sk->d_hash, sk->n * 8, cudaMemcpyDeviceToHost));
     if (sk->n && counts) CK(cudaMemcpy(counts, sk->d_cnt, sk->n * 4, cudaMemcpyDeviceToHost));
     return AC_OK;
 }
 extern "C" void ac_sketch_free(ac_sketch *sk) {
     if (!sk) return;
-    cudaSetDevice(sk->ctx->dev);
+    cudaSetDevice(sk->dev);
     cudaFree(sk->d_hash); cudaFree(sk->d_cnt);
     delete sk;
 }
@@ -879,7 +889,7 @@ extern "C" int ac_refs_load(ac_ctx *c, const uint64_t *hashes, const uint64_t *o
         max_n = std::max<uint64_t>(max_n, offsets[i + 1] - offsets[i]);
     }
     ac_refs *r = new ac_refs();
-    r->ctx = c; r->n_refs = n_refs; r->k = k; r->s = sketch_size; r->hash_bits = hash_bits; r->max_n = max_n;
+    r->ctx = c; r->dev = c->dev; r->n_refs = n_refs; r->k = k; r->s = sketch_size; r->hash_bits = hash_bits; r->max_n = max_n;
     r->d_hash = r->d_off = r->d_len = nullptr;
     cudaError_t e = cudaMalloc(&r->d_hash, (total ? total : 1) * 8);
     if (e == cudaSuccess) e = cudaMalloc(&r->d_off, (size_t)(n_refs + 1) * 8);
@@ -894,7 +904,7 @@ extern "C" int ac_refs_load(ac_ctx *c, const uint64_t *hashes, const uint64_t *o
 extern "C" int ac_refs_count(const ac_refs *r) { return r ? r->n_refs : 0; }
 extern "C" void ac_refs_free(ac_refs *r) {
     if (!r) return;
-    cudaSetDevice(r->ctx->dev);
+    cudaSetDevice(r->dev);
     cudaFree(r->d_hash); cudaFree(r->d_off); cudaFree(r->d_len);
     delete r;
 }

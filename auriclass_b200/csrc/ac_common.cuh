@@ -118,6 +118,15 @@ void launch_finalize(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, int 
 // sort (hash,count) pairs, sum equal hashes, keep count >= m; result in keys_a/vals_a, n in jd->n_unique
 void launch_merge_counts(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, uint64_t n, int min_copies);
 
+constexpr int MAX_RANGES = 64;  // hash ranges (= ranks) of the multi-GPU exchange
+struct RangeBounds {             // passed by value
+    unsigned long long b[MAX_RANGES];  // b[r] = first hash owned by range r
+    unsigned long long tau_cut;
+    int n;
+};
+void launch_table_ranges(const LaunchCtx &lc, const SelectBufs &sb, uint32_t n_table, const RangeBounds &bounds,
+                         unsigned long long *d_out /*[n+1], device*/);
+
 void launch_dist(const LaunchCtx &lc, const unsigned long long *ref_hashes, const unsigned long long *ref_off,
                  const unsigned long long *ref_len, int n_refs, const unsigned long long *const *q_hashes,
                  const unsigned long long *q_n, const unsigned long long *q_len, int n_q, int k,

@@ -319,6 +319,22 @@ __global__ void __launch_bounds__(1024) k4_finalize(const u64 *__restrict__ sk_h
     }
 }
 
+// multi-GPU hash-range split: out[r] = first table entry >= bounds.b[r] (r < n), out[n] = first entry > tau_cut
+__global__ void k3_table_ranges(const u64 *__restrict__ tab_hash, uint32_t n_table, RangeBounds bounds,
+                                unsigned long long *__restrict__ out) {
+    const int r = threadIdx.x;
+    if (r > bounds.n) return;
+    const bool upper = r == bounds.n;          // last boundary: upper_bound(tau_cut)
+    const u64 key = upper ? bounds.tau_cut : bounds.b[r];
+    uint32_t lo = 0, hi = n_table;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const u64 v = tab_hash[mid];
+        if (upper ? (v <= key) : (v < key)) lo = mid + 1; else hi = mid;
+    }
+    out[r] = lo;
+}
+
 void runs_and_qualify(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, const u64 *keys, const uint32_t *vals,
                       uint32_t n, int sketch_size, int min_copies, u64 *out_hash, uint32_t *out_cnt, int compact) {
     const uint32_t n_tiles = div_up(n ? n : 1, SC_TILE);
@@ -350,6 +366,12 @@ void launch_consolidate(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, u
 
 void launch_finalize(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, int use64) {
     k4_finalize<<<1, 1024, 0, lc.stream>>>(sb.sk_hash, sb.sk_cnt, jd, use64);
+    ++*lc.launches;
+}
+
+void launch_table_ranges(const LaunchCtx &lc, const SelectBufs &sb, uint32_t n_table, const RangeBounds &bounds,
+                         unsigned long long *d_out) {
+    k3_table_ranges<<<1, MAX_RANGES + 1, 0, lc.stream>>>(sb.tab_hash, n_table, bounds, d_out);
     ++*lc.launches;
 }
 

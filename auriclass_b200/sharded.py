@@ -1,0 +1,190 @@
+"""Read-block sharded `mash sketch -r -m` over the GPUs of one box (BASELINE.json configs[2]).
+
+Every rank parses and hashes its own read blocks (ac_sketch_begin/feed on its GPU) and ends with an
+exact local table {hash <= tau_r : local count}.  The sketch Mash would have produced from all the
+reads is bottom-s of {h : sum over ranks of count_r(h) >= m} (the result is
+order independent), so one exchange step makes the counts exact:
+
+  1. tau_cut = min_r tau_r                       (all-reduce MIN, 8 bytes)
+     every rank holds exact local counts of everything <= tau_cut, and the rank that attained the
+     minimum proves >= s qualified hashes exist below it (or tau_cut is the whole hash space).
+  2. hash-range exchange                         (all-to-all: counts, then hashes and counts)
+     [0, tau_cut] is cut into P equal ranges; range r is owned by rank r.  Hashes are uniform, so
+     the ranges balance.  Volume: the local tables, ~1e5..1e6 entries of 12 bytes per rank.
+  3. owner merge: sum counts of equal hashes, keep >= m, sort   (ac_merge_counts: CUDA radix sort + run sums)
+  4. all-gather of the owners' first <= s qualified entries; the ordered concatenation's first s
+     entries are the sketch                      (ac_sketch_from_table: K4 estimates)
+
+The collectives go through torch.distributed (NCCL over NVLink on the GPUs; gloo in the CPU tests of
+this host logic).  There is no fused compute+collective kernel: the exchange moves about a megabyte
+once per isolate, after the last hash kernel has finished, so there is nothing to overlap.
+
+The arithmetic sits behind a small backend interface so the same exchange logic runs in
+tests/test_sharded_gloo.py with tables made by the CPU oracle; the product backend is
+`CudaTableBackend` (libauriclass_cuda.so) and nothing else.
+
+Replaces: `mash sketch -r -m M` at /root/reference/auriclass/classes.py:576-596 for inputs large
+enough to shard (the reference itself is single process, docs/running_analysis.md:47-60).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import SketchInfo, check
+
+_SIGN = -(1 << 63)  # u64 -> order-preserving i64: x ^ 0x8000_0000_0000_0000
+
+
+def u64_to_ordered_i64(x: int) -> int:
+    x &= (1 << 64) - 1
+    y = x ^ (1 << 63)
+    return y - (1 << 64) if y >= (1 << 63) else y
+
+
+def ordered_i64_to_u64(y: int) -> int:
+    return (y & ((1 << 64) - 1)) ^ (1 << 63)
+
+
+def range_bounds(tau_cut: int, n_ranges: int) -> List[int]:
+    """b[r] = first hash owned by range r over [0, tau_cut]: owner(x) = floor(x * P / (tau_cut + 1))."""
+    span = tau_cut + 1
+    return [(span * r + n_ranges - 1) // n_ranges for r in range(n_ranges)]
+
+
+@dataclass
+class LocalTable:
+    """A rank's exact (hash, count) table of everything <= tau, ascending; bit patterns of u64 / u32
+    carried in int64 / int32 tensors (torch collectives have no unsigned 64-bit type)."""
+    hashes: torch.Tensor   # int64, device of the backend
+    counts: torch.Tensor   # int32
+    tau: int
+    counters: Tuple[int, ...] = (0, 0, 0, 0, 0)  # n_records, n_kept, total_len, n_kmers, n_candidates
+
+
+class CudaTableBackend:
+    """libauriclass_cuda.so on this rank's GPU."""
+
+    def __init__(self, engine):
+        self.eng = engine
+        self.lib = engine.lib
+        self.device = torch.device("cuda", engine.device)
+
+    def local_table(self, job: int, tau_cut_fn, n_ranges: int):
+        """End the local pass; returns (send splits, LocalTable restricted to <= tau_cut)."""
+        n = C.c_uint64()
+        tau = C.c_uint64()
+        spec = C.c_int()
+        info = SketchInfo()
+        try:
+            check(self.lib.ac_sketch_end_local(job, C.byref(n), C.byref(tau), C.byref(spec), C.byref(info)))
+            tau_cut = tau_cut_fn(int(tau.value))
+            begins = (C.c_uint64 * (n_ranges + 1))()
+            check(self.lib.ac_job_table_ranges(job, tau_cut, n_ranges, begins))
+            b = [int(x) for x in begins]
+            n_send = b[n_ranges]
+            h = torch.empty(max(n_send, 1), dtype=torch.int64, device=self.device)
+            c = torch.empty(max(n_send, 1), dtype=torch.int32, device=self.device)
+            check(self.lib.ac_job_table_export(job, 0, n_send, h.data_ptr(), c.data_ptr()))
+        finally:
+            self.lib.ac_sketch_abort(job)  # frees the job; the exported copy is ours
+        splits = [b[r + 1] - b[r] for r in range(n_ranges)]
+        counters = (info.n_records, info.n_kept, info.total_len, info.n_kmers, info.n_candidates)
+        return splits, LocalTable(h[:n_send], c[:n_send], tau_cut, counters)
+
+    def merge_counts(self, hashes: torch.Tensor, counts: torch.Tensor, min_copies: int) -> int:
+        """In place: sum equal hashes, keep count >= m, ascending.  Returns the number kept."""
+        n_out = C.c_uint64()
+        n = hashes.numel()
+        if n == 0:
+            return 0
+        torch.cuda.current_stream(self.device).synchronize()  # NCCL wrote these on torch's stream; the library has its own
+        check(self.lib.ac_merge_counts(self.eng.ctx, hashes.data_ptr(), counts.data_ptr(), n, min_copies, C.byref(n_out)))
+        return int(n_out.value)
+
+    def build_sketch(self, hashes: torch.Tensor, counts: torch.Tensor, k: int, s: int, name: str):
+        from .mash_gpu import GpuSketch
+        sk = C.c_void_p()
+        info = SketchInfo()
+        torch.cuda.current_stream(self.device).synchronize()
+        check(self.lib.ac_sketch_from_table(self.eng.ctx, hashes.data_ptr(), counts.data_ptr(), hashes.numel(), k, s,
+                                            C.byref(sk), C.byref(info)))
+        return GpuSketch(self.eng, sk.value, info, name, k, s)
+
+
+class ShardedSketcher:
+    """The exchange protocol (steps 1-4 above) over a torch.distributed process group."""
+
+    def __init__(self, engine, rank: int, world: int, group: Optional[dist.ProcessGroup] = None, backend=None):
+        self.rank, self.world, self.group = rank, world, group
+        self.backend = backend if backend is not None else CudaTableBackend(engine)
+        self.device = self.backend.device
+        self.last_exchange = {}
+
+    # -- step 1
+    def _tau_cut(self, tau_local: int) -> int:
+        t = torch.tensor([u64_to_ordered_i64(tau_local)], dtype=torch.int64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return ordered_i64_to_u64(int(t.item()))
+
+    def finish(self, job, k: int, s: int, m: int, name: str = "reads"):
+        """Collective: every rank calls it with its own job; every rank returns the same sketch."""
+        P = self.world
+        splits, tab = self.backend.local_table(job, self._tau_cut, P)
+        # -- step 2: sizes, then payload
+        send_n = torch.tensor(splits, dtype=torch.int64, device=self.device)
+        recv_n = torch.empty(P, dtype=torch.int64, device=self.device)
+        dist.all_to_all_single(recv_n, send_n, group=self.group)
+        rsplits = [int(x) for x in recv_n.tolist()]
+        n_recv = sum(rsplits)
+        rh = torch.empty(max(n_recv, 1), dtype=torch.int64, device=self.device)[:n_recv]
+        rc = torch.empty(max(n_recv, 1), dtype=torch.int32, device=self.device)[:n_recv]
+        dist.all_to_all_single(rh, tab.hashes, rsplits, splits, group=self.group)
+        dist.all_to_all_single(rc, tab.counts, rsplits, splits, group=self.group)
+        # -- step 3: owner merge (exact counts of this rank's hash range)
+        n_q = self.backend.merge_counts(rh, rc, m)
+        n_keep = min(n_q, s)
+        # -- step 4: gather the owners' prefixes and the job counters
+        meta = torch.tensor([n_keep, n_q, *tab.counters], dtype=torch.int64, device=self.device)
+        metas = torch.empty(P * meta.numel(), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(metas, meta, group=self.group)
+        metas = metas.view(P, -1).tolist()
+        keeps = [int(r[0]) for r in metas]
+        pad = max(max(keeps), 1)
+        sh = torch.zeros(pad, dtype=torch.int64, device=self.device)
+        sc = torch.zeros(pad, dtype=torch.int32, device=self.device)
+        sh[:n_keep] = rh[:n_keep]
+        sc[:n_keep] = rc[:n_keep]
+        gh = torch.empty(P * pad, dtype=torch.int64, device=self.device)
+        gc = torch.empty(P * pad, dtype=torch.int32, device=self.device)
+        dist.all_gather_into_tensor(gh, sh, group=self.group)
+        dist.all_gather_into_tensor(gc, sc, group=self.group)
+        # ordered concatenation (range r < range r+1), first s entries
+        parts_h, parts_c, left = [], [], s
+        for r in range(P):
+            take = min(keeps[r], left)
+            if take:
+                parts_h.append(gh[r * pad:r * pad + take])
+                parts_c.append(gc[r * pad:r * pad + take])
+                left -= take
+        if parts_h:
+            fh, fc = torch.cat(parts_h).contiguous(), torch.cat(parts_c).contiguous()
+        else:
+            fh = torch.empty(0, dtype=torch.int64, device=self.device)
+            fc = torch.empty(0, dtype=torch.int32, device=self.device)
+        total_q = sum(int(r[1]) for r in metas)
+        self.last_exchange = {"tau_cut": tab.tau, "sent": sum(splits), "received": n_recv, "qualified_owned": n_q,
+                              "qualified_total": total_q}
+        if fh.numel() == 0:
+            raise _lib.NoRecordsError(_lib.AC_E_NO_RECORDS, "did not find sequence records (no hash reached the minimum copy number on any rank)")
+        sk = self.backend.build_sketch(fh, fc, k, s, name)
+        # whole-job counters (sums over ranks)
+        for i, key in enumerate(("n_records", "n_kept", "total_len", "n_kmers", "n_candidates")):
+            sk.info[key] = sum(int(r[2 + i]) for r in metas)
+        sk.info["final_tau"] = tab.tau
+        return sk

@@ -134,7 +134,10 @@ def cpu_sketch(buf: np.ndarray, threads: int = 0):
     return oracle.sketch_parallel([buf.tobytes() if not isinstance(buf, bytes) else buf], K, S, M, threads=threads)
 
 
-def cpu_baseline_sample(text: np.ndarray, n_reads_sample: int, rec: int) -> dict:
+def cpu_baseline_sample(text: np.ndarray, n_reads_sample: int, rec: int, n_reads_stream: int = 150_000) -> dict:
+    """The oracle (CPU restatement of Mash; the mash binary is not installed) on this box's host cores:
+    all cores over `n_reads_sample` reads (value), plus the faithful single-thread streaming MinHashHeap
+    -- what `mash sketch -r -m` without -p, i.e. AuriClass today, executes -- on a smaller sample."""
     from oracle import oracle
     sample = text[: n_reads_sample * rec].tobytes()
     cores = oracle.num_threads()
@@ -142,10 +145,19 @@ def cpu_baseline_sample(text: np.ndarray, n_reads_sample: int, rec: int) -> dict
     sk = oracle.sketch_parallel([sample], K, S, M)
     dt = time.perf_counter() - t0
     bases = n_reads_sample * READ_LEN
-    return {"value": bases / dt / 1e9, "unit": "Gbases/s", "cores": cores, "kind": "port",
-            "sample": f"first {n_reads_sample} reads of the workload ({bases / 1e6:.1f} Mbp, {len(sample) / 1e6:.0f} MB FASTQ), "
-                      f"oracle.sketch_parallel (restated-Mash CPU baseline, not the mash binary), {dt:.2f} s",
-            "n_hashes": int(len(sk.hashes))}
+    out = {"value": bases / dt / 1e9, "unit": "Gbases/s", "cores": cores, "kind": "port",
+           "sample": f"first {n_reads_sample} reads of the workload ({bases / 1e6:.1f} Mbp, {len(sample) / 1e6:.0f} MB FASTQ), "
+                     f"oracle.sketch_parallel (restated-Mash CPU baseline, not the mash binary), {dt:.2f} s wall = "
+                     f"{dt * cores:.0f} core-seconds",
+           "n_hashes": int(len(sk.hashes))}
+    n1 = min(n_reads_sample, n_reads_stream)
+    small = text[: n1 * rec].tobytes()
+    t0 = time.perf_counter()
+    oracle.sketch_stream([small], K, S, M)
+    dt1 = time.perf_counter() - t0
+    out["single_thread_stream"] = {"value": n1 * READ_LEN / dt1 / 1e9, "unit": "Gbases/s", "cores": 1,
+                                   "sample": f"first {n1} reads, oracle.sketch_stream (faithful streaming MinHashHeap), {dt1:.2f} s"}
+    return out
 
 
 def run_reference_arm(args) -> None:
@@ -155,7 +167,10 @@ def run_reference_arm(args) -> None:
     from auriclass_b200 import synth
     from oracle import oracle
     rec = synth.record_bytes(READ_LEN, 0)
-    n_sample = min(args.reads, args.ref_sample_reads)
+    n_sample = args.ref_sample_reads or args.reads
+    if not args.ref_sample_reads and args.steps + args.warmup > 40:   # keep the whole run within a few minutes
+        n_sample = max(100_000, args.reads * 40 // (args.steps + args.warmup))
+    n_sample = min(args.reads, n_sample)
     text, contigs = make_reads(n_sample, SEED_READS, 0, lambda n: np.empty(n, np.uint8))
     sample = text.tobytes()
     cores = oracle.num_threads()
@@ -200,8 +215,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=N_READS_C2, help="reads per rank (default: the C2 workload)")
-    ap.add_argument("--ref-sample-reads", type=int, default=400_000)
-    ap.add_argument("--cpu-sample-reads", type=int, default=400_000)
+    ap.add_argument("--ref-sample-reads", type=int, default=0, help="reads per reference-arm step (0: whole workload, shrunk if steps+warmup > 40)")
+    ap.add_argument("--cpu-sample-reads", type=int, default=N_READS_C2)
     ap.add_argument("--n-refs", type=int, default=24)
     ap.add_argument("--no-dist", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -368,7 +383,7 @@ def main() -> None:
         # K2 algorithmic bytes per step: the base stream (1 B per base + 1 separator per read) in, 8 B per candidate out
         k2_bytes = bases_per_rank + n_rec + 8 * n_cand
         hash_s = prof["hash_ms"] * 1e-3
-        n_seg = -(-nbytes // (32 << 20))
+        n_seg = -(-nbytes // (int(os.environ.get("AC_SEG_MB", "128")) << 20))  # K2 launches per step = segments (ac_common.cuh SEG_BYTES)
         traffic = None
         tp = ROOT / "profiles" / "k2_traffic.json"
         if tp.exists():

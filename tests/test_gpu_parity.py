@@ -371,3 +371,75 @@ def test_launch_counter_counts_our_kernels(engine, reads):
     n0 = engine.launch_count()
     engine.sketch_bytes([reads[0]], k=27, s=1000, m=1)
     assert engine.launch_count() - n0 >= 5
+
+
+# ------------------------------------------------------------------ multi-GPU exchange: CUDA backend pieces
+def _split_fastq(fq: bytes, parts: int):
+    lines = fq.split(b"\n")[:-1]
+    recs = [b"\n".join(lines[i:i + 4]) + b"\n" for i in range(0, len(lines), 4)]
+    per = -(-len(recs) // parts)
+    return [b"".join(recs[r * per:(r + 1) * per]) for r in range(parts)]
+
+
+@pytest.mark.parametrize("P,s,m", [(2, 1000, 3), (3, 50000, 3), (4, 2000, 2)])
+def test_sharded_cuda_backend_emulated_ranks(engine, reads, P, s, m):
+    """P ranks emulated one after the other on one GPU: every rank's local table (ac_sketch_end_local),
+    the hash-range split (ac_job_table_ranges / _export), the owner merge (ac_merge_counts) and the
+    final sketch (ac_sketch_from_table) are the CUDA entry points the NCCL path uses; the exchange
+    itself is done with torch indexing here.  Result must equal the oracle on all reads together."""
+    import torch
+    from auriclass_b200.sharded import CudaTableBackend
+    be = CudaTableBackend(engine)
+    fq = reads[0] + reads[1]
+    shards = _split_fastq(fq, P)
+
+    def job_for(buf):
+        job = engine._begin(27, s, 42, m, AC_MODE_READS)
+        a = np.frombuffer(buf, np.uint8)
+        _lib.check(engine.lib.ac_sketch_feed(job, a.ctypes.data, a.size, 0, 1))
+        return job
+
+    taus = []
+    for buf in shards:   # dry run: learn every rank's threshold (the all-reduce MIN of the real path)
+        _, t = be.local_table(job_for(buf), lambda tau: tau, P)
+        taus.append(t.tau)
+    tau_cut = min(taus)
+    tables = [be.local_table(job_for(buf), lambda tau: tau_cut, P) for buf in shards]
+    owned_h, owned_c, keeps = [], [], []
+    for r in range(P):   # all-to-all: owner r receives slice r of every rank's table
+        hs, cs = [], []
+        for splits, t in tables:
+            o = sum(splits[:r])
+            hs.append(t.hashes[o:o + splits[r]]); cs.append(t.counts[o:o + splits[r]])
+        h, c = torch.cat(hs).contiguous(), torch.cat(cs).contiguous()
+        n_q = be.merge_counts(h, c, m)
+        owned_h.append(h[:n_q]); owned_c.append(c[:n_q]); keeps.append(n_q)
+    fh, fc = torch.cat(owned_h)[:s].contiguous(), torch.cat(owned_c)[:s].contiguous()
+    sk = be.build_sketch(fh, fc, 27, s, "emulated")
+    ref = oracle.sketch([fq], 27, s, m)
+    h, c = sk.hashes()
+    assert np.array_equal(h, ref.hashes) and np.array_equal(c, ref.counts)
+    assert sk.genome_size == ref.genome_size and sk.coverage == ref.coverage
+    assert sum(t.counters[3] for _, t in tables) == ref.n_kmers
+
+
+def test_sharded_nccl_world1(engine, reads):
+    """The real ShardedSketcher over an NCCL process group of one rank (all collectives run)."""
+    import os
+    import torch
+    import torch.distributed as dist
+    from auriclass_b200.sharded import ShardedSketcher
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29731")
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        sh = ShardedSketcher(engine, 0, 1)
+        job = engine._begin(27, 50000, 42, 3, AC_MODE_READS)
+        for i, b in enumerate(reads):
+            a = np.frombuffer(b, np.uint8)
+            _lib.check(engine.lib.ac_sketch_feed(job, a.ctypes.data, a.size, i, 1))
+        sk = sh.finish(job, 27, 50000, 3)
+        assert_same_sketch(sk, oracle.sketch(reads, 27, 50000, 3))
+    finally:
+        dist.destroy_process_group()
