@@ -58,9 +58,10 @@ struct ac_ctx {
     size_t seg_bytes;          // raw text per segment (SEG_BYTES, or AC_SEG_MB for tests)
     SelectBufs sb;
     bool sb_ok;
-    uint8_t *d_Z;
-    TileSum *d_sums;
-    TileIn *d_tin;
+    uint8_t *d_Z[2];           // base stream of the segment in flight, ping-pong by segment parity
+    unsigned long long *d_st1, *d_st2;  // K1 look-back status words (state, output offset), one per tile
+    uint32_t seg_epoch;        // serial of the last segment launched on this context (tags the status words)
+    size_t max_tiles;
     JobDev *d_jd, *h_jd;
     std::vector<Slab> slabs;
     size_t cur_slab;
@@ -99,6 +100,7 @@ struct ac_job {
     uint32_t n_table_host;
     unsigned long long tau_host;
     size_t bytes_done, next_mark;
+    uint32_t seg_serial, ticket_base; // segments / K1 tiles launched in the current pass
     bool ended_local;
 };
 
@@ -218,10 +220,11 @@ extern "C" int ac_create(int device, ac_ctx **out) {
     if (c->seg_bytes > ((size_t)1 << 30)) c->seg_bytes = (size_t)1 << 30;
     CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
-    CK(cudaMalloc(&c->d_Z, Z_CARRY + c->seg_bytes + K2_TILE + 4096));
-    const size_t max_tiles = c->seg_bytes / K1_TILE + 4;
-    CK(cudaMalloc(&c->d_sums, max_tiles * sizeof(TileSum)));
-    CK(cudaMalloc(&c->d_tin, max_tiles * sizeof(TileIn)));
+    for (int i = 0; i < 2; i++) CK(cudaMalloc(&c->d_Z[i], Z_CARRY + c->seg_bytes + K2_TILE + 4096));
+    c->max_tiles = c->seg_bytes / K1_TILE + 4;
+    CK(cudaMalloc(&c->d_st1, c->max_tiles * 8)); CK(cudaMalloc(&c->d_st2, c->max_tiles * 8));
+    CK(cudaMemset(c->d_st1, 0, c->max_tiles * 8)); CK(cudaMemset(c->d_st2, 0, c->max_tiles * 8));
+    c->seg_epoch = 0;
     CK(cudaMalloc(&c->d_jd, sizeof(JobDev)));
     CK(cudaHostAlloc(&c->h_jd, sizeof(JobDev), cudaHostAllocDefault));
     CK(cudaEventCreate(&c->ev_job0)); CK(cudaEventCreate(&c->ev_job1));
@@ -235,7 +238,7 @@ extern "C" void ac_destroy(ac_ctx *c) {
     if (c->active) ac_sketch_abort(c->active);  // a job cannot outlive its context
     cudaDeviceSynchronize();
     free_select(c);
-    cudaFree(c->d_Z); cudaFree(c->d_sums); cudaFree(c->d_tin); cudaFree(c->d_jd); cudaFreeHost(c->h_jd);
+    cudaFree(c->d_Z[0]); cudaFree(c->d_Z[1]); cudaFree(c->d_st1); cudaFree(c->d_st2); cudaFree(c->d_jd); cudaFreeHost(c->h_jd);
     for (auto &s : c->slabs) cudaFree(s.ptr);
     cudaFree(c->d_dist); cudaFree(c->d_p); cudaFree(c->d_common); cudaFree(c->d_denom); cudaFree(c->d_qmeta);
     cudaFreeHost(c->h_dist); cudaFreeHost(c->h_p); cudaFreeHost(c->h_common); cudaFreeHost(c->h_denom); cudaFreeHost(c->h_qmeta);
@@ -385,9 +388,10 @@ static int start_pass(ac_job *j, unsigned long long tau0, bool safe) {
     ac_ctx *c = j->ctx;
     JobDev z;
     memset(&z, 0, sizeof(z));
-    z.at_line_start = 1;
+    z.ps[0].at_line_start = 1;
+    z.ps[0].n_zbuf = Z_CARRY;
     z.tau = tau0;
-    z.n_zbuf = Z_CARRY;
+    j->seg_serial = 0; j->ticket_base = 0;
     *c->h_jd = z;
     CK(cudaMemcpyAsync(c->d_jd, c->h_jd, sizeof(JobDev), cudaMemcpyHostToDevice, c->s_comp));
     CK(cudaStreamSynchronize(c->s_comp));
@@ -418,19 +422,31 @@ static int run_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_o
     sd.base = (const uint8_t *)(addr & ~(uintptr_t)15);
     sd.skip = (uint32_t)(addr & 15);
     sd.len = (uint32_t)seg_len;
-    sd.n_tiles = seg_len ? div_up(sd.skip + seg_len, K1_TILE) : 0;
+    sd.n_tiles = seg_len ? div_up(sd.skip + seg_len, K1_TILE) : 1;  // an empty segment still threads the parser state
     sd.append_nl = append_nl ? 1 : 0;
     sd.fmt = p.fmt;
     sd.first_of_stream = j->first_of_stream ? 1 : 0;
     sd.last_of_file = last_of_file ? 1 : 0;
+    sd.serial = j->seg_serial;
+    if (++c->seg_epoch >= (1u << 30)) {  // status-word tags wrapped: start over with clean arrays
+        CK(cudaMemsetAsync(c->d_st1, 0, c->max_tiles * 8, c->s_comp)); CK(cudaMemsetAsync(c->d_st2, 0, c->max_tiles * 8, c->s_comp));
+        c->seg_epoch = 1;
+    }
+    sd.epoch = c->seg_epoch;
+    sd.ticket_base = j->ticket_base;
+    if (sd.n_tiles > c->max_tiles) return fail(AC_E_INTERNAL, "segment of %zu bytes exceeds the tile arrays", seg_len);
+    uint8_t *Z = c->d_Z[sd.serial & 1u];
     {
         ProfScope ps(c, 0);
-        launch_parse_segment(lc, sd, c->d_sums, c->d_tin, c->d_jd, c->d_Z);
+        launch_parse_segment(lc, sd, c->d_st1, c->d_st2, c->d_jd, c->d_Z[(sd.serial + 1u) & 1u], Z);
     }
     {
         ProfScope ps(c, 1);
-        launch_hash_segment(lc, j->k, c->d_Z, (uint32_t)(Z_CARRY + seg_len + 1), c->d_jd, c->sb.keys_a, c->sb.cap, j->seed, j->use64);
+        launch_hash_segment(lc, j->k, Z, (uint32_t)(Z_CARRY + seg_len + 1), (int)((sd.serial + 1u) & 1u), c->d_jd, c->sb.keys_a,
+                            c->sb.cap, j->seed, j->use64);
     }
+    j->seg_serial++;
+    j->ticket_base += sd.n_tiles;
     CK(cudaGetLastError());
     j->first_of_stream = false;
     j->cand_bound += seg_bound;
@@ -659,10 +675,12 @@ static int finish_local(ac_job *j) {
         rc = read_jd(c);
         if (rc) return rc;
         const JobDev &h = *c->h_jd;
-        if (h.format_error) {
-            const char *what = (h.format_error & FERR_FQ_HEADER) ? "a FASTQ record does not start with '@' (multi-line FASTQ is not supported)"
-                             : (h.format_error & FERR_FQ_PLUS) ? "third line of a FASTQ record does not start with '+' (multi-line FASTQ is not supported)"
-                             : (h.format_error & FERR_FQ_TRUNC) ? "FASTQ input is truncated or sequence/quality lengths differ"
+        uint32_t ferr = h.format_error;
+        if (h.fq_seq_bytes != h.fq_qual_bytes) ferr |= FERR_FQ_TRUNC;  // sequence and quality byte totals of the job differ
+        if (ferr) {
+            const char *what = (ferr & FERR_FQ_HEADER) ? "a FASTQ record does not start with '@' (multi-line FASTQ is not supported)"
+                             : (ferr & FERR_FQ_PLUS) ? "third line of a FASTQ record does not start with '+' (multi-line FASTQ is not supported)"
+                             : (ferr & FERR_FQ_TRUNC) ? "FASTQ input is truncated or sequence/quality lengths differ"
                              : "'+' line inside FASTA input";
             return fail(AC_E_FORMAT, "input rejected by the GPU parser: %s", what);
         }

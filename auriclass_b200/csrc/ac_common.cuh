@@ -31,36 +31,29 @@ struct SegDesc {
     const uint8_t *base;  // 16-byte aligned (aligned-down) device pointer
     uint32_t skip;        // leading bytes of the aligned range that precede the segment
     uint32_t len;         // segment bytes incl. the virtual newline when append_nl
-    uint32_t n_tiles;
+    uint32_t n_tiles;     // >= 1
     int32_t append_nl;    // the last byte of the segment is a virtual '\n' (file lacks a final newline)
     int32_t fmt;          // FMT_*
     int32_t first_of_stream;  // first segment of the job's base stream: carry is all separators
     int32_t last_of_file;
+    uint32_t serial;      // segment number within the pass: parity selects the ParseState slot and the Z buffer
+    uint32_t epoch;       // context-wide segment serial (< 2^30, never reused): tags the look-back status words
+    uint32_t ticket_base; // tiles handed out by earlier segments of the pass (JobDev::tile_ticket keeps counting)
 };
 
-// pass A -> scan: what a tile contributes under every possible incoming state
-struct TileSum {
-    uint32_t a;       // FASTQ: newline count.  FASTA: bit0 has line start, bit1 type of the last line start (1 = sequence)
-    uint32_t c[4];    // FASTQ: bytes in lines with local index = r (mod 4).  FASTA: c[0] head emit (if sequence), c[1] rest emit
-    uint32_t ends_nl; // last valid byte of the tile is '\n'
-};
-// scan -> pass C
-struct TileIn {
-    uint32_t state;    // FASTQ: phase (0 header,1 sequence,2 plus,3 quality) of the line holding the tile's first byte
-                       // FASTA: type of that line (0 header, 1 sequence)
-    uint32_t out_off;  // where the tile's first emitted byte lands in the Z buffer
-    uint32_t first_ls; // the tile's first valid byte begins a line (tile 0 only; other tiles peek)
+// Parser state between segments; double buffered (segment i reads slot i&1, writes slot (i+1)&1)
+struct ParseState {
+    uint32_t fq_phase;       // FASTQ: phase (0 header,1 sequence,2 plus,3 quality) of the line holding the next byte
+    uint32_t fa_type;        // FASTA: type of that line (0 header, 1 sequence)
+    uint32_t at_line_start;  // the next byte begins a line
+    uint32_t n_zbuf;         // Z_CARRY + bytes the segment emitted into its Z buffer
 };
 
 // Device-resident job state, updated by kernels, read back by the host at sync points.
 struct JobDev {
-    // parser state of the file being read
-    uint32_t fq_phase;
-    uint32_t fa_type;
-    uint32_t at_line_start;
+    ParseState ps[2];
+    uint32_t tile_ticket;   // K1 tile dispenser (monotonic over the pass)
     uint32_t format_error;
-    // base stream of the current segment
-    uint32_t n_zbuf;  // Z_CARRY + bytes emitted by the segment
     uint32_t overflow;  // candidate buffer overflowed (pass must be repeated in safe mode)
     // counters over the whole job
     unsigned long long fq_seq_bytes, fq_qual_bytes;
@@ -92,9 +85,10 @@ struct LaunchCtx {
 };
 
 // kernels' host-side launchers (defined in the .cu files)
-void launch_parse_segment(const LaunchCtx &lc, const SegDesc &sd, TileSum *sums, TileIn *tin, JobDev *jd,
-                          uint8_t *Z);
-void launch_hash_segment(const LaunchCtx &lc, int k, const uint8_t *Z, uint32_t max_zbuf, JobDev *jd,
+void launch_parse_segment(const LaunchCtx &lc, const SegDesc &sd, unsigned long long *st1, unsigned long long *st2,
+                          JobDev *jd, const uint8_t *Zprev, uint8_t *Z);
+// ps_slot: ParseState slot holding this segment's n_zbuf (= (serial + 1) & 1)
+void launch_hash_segment(const LaunchCtx &lc, int k, const uint8_t *Z, uint32_t max_zbuf, int ps_slot, JobDev *jd,
                          unsigned long long *cand, unsigned long long cand_cap, uint32_t seed, int use64);
 
 struct SelectBufs {

@@ -84,7 +84,7 @@ constexpr int K2_TB = K2_TILE + 64;             // tile bytes staged in shared m
 template <int K>
 __global__ void __launch_bounds__(K2_THREADS, 4) k2_hash(const uint8_t *__restrict__ Z, JobDev *__restrict__ jd,
                                                          unsigned long long *__restrict__ cand,
-                                                         unsigned long long cand_cap, uint32_t seed, int use64) {
+                                                         unsigned long long cand_cap, uint32_t seed, int ps_slot) {
     __shared__ __align__(128) uint8_t s_fwd[K2_TB + 64];  // base stream bytes of the tile (TMA destination)
     __shared__ __align__(16) uint8_t s_rc[K2_TB + 64];    // reverse complement of the tile: s_rc[p'] = comp(s_fwd[TB-1-p'])
     __shared__ uint32_t s_valid[K2_TB / 32 + 2];          // bit b of word c: byte 32c+b is a valid base
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(K2_THREADS, 4) k2_hash(const uint8_t *__restri
     __shared__ unsigned long long s_stat[5];  // kmers, records, kept, short_len, bases
     __shared__ __align__(8) uint64_t s_bar;
 
-    const uint32_t n_zbuf = jd->n_zbuf;
+    const uint32_t n_zbuf = jd->ps[ps_slot].n_zbuf;
     const long long n_win = (long long)n_zbuf - K + 1;             // window starts 0 .. n_win-1 exist
     const long long tile_start = (long long)blockIdx.x * K2_TILE;
     // a tile is needed while it holds window starts; record-end positions p = start + K < n_zbuf
@@ -230,19 +230,20 @@ __global__ void __launch_bounds__(K2_THREADS, 4) k2_hash(const uint8_t *__restri
 }
 
 template <int K>
-void launch_k(const LaunchCtx &lc, const uint8_t *Z, uint32_t max_zbuf, JobDev *jd, unsigned long long *cand,
-              unsigned long long cand_cap, uint32_t seed, int use64) {
+void launch_k(const LaunchCtx &lc, const uint8_t *Z, uint32_t max_zbuf, int ps_slot, JobDev *jd, unsigned long long *cand,
+              unsigned long long cand_cap, uint32_t seed) {
     const unsigned grid = div_up(max_zbuf, K2_TILE);
-    k2_hash<K><<<grid, K2_THREADS, 0, lc.stream>>>(Z, jd, cand, cand_cap, seed, use64);
+    k2_hash<K><<<grid, K2_THREADS, 0, lc.stream>>>(Z, jd, cand, cand_cap, seed, ps_slot);
     ++*lc.launches;
 }
 
 }  // namespace
 
-#define AC_K_CASE(KK) case KK: launch_k<KK>(lc, Z, max_zbuf, jd, cand, cand_cap, seed, use64); break;
+#define AC_K_CASE(KK) case KK: launch_k<KK>(lc, Z, max_zbuf, ps_slot, jd, cand, cand_cap, seed); break;
 
-void launch_hash_segment(const LaunchCtx &lc, int k, const uint8_t *Z, uint32_t max_zbuf, JobDev *jd,
+void launch_hash_segment(const LaunchCtx &lc, int k, const uint8_t *Z, uint32_t max_zbuf, int ps_slot, JobDev *jd,
                          unsigned long long *cand, unsigned long long cand_cap, uint32_t seed, int use64) {
+    (void)use64;  // the hash width follows k (CandSink<(K > 16)>)
     switch (k) {
 #ifdef AC_ONLY_K27  // development builds: one instantiation, seconds to compile
         AC_K_CASE(27)

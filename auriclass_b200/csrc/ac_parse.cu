@@ -1,16 +1,21 @@
-// ac_parse.cu -- kernel K1: FASTA / FASTQ record parser.
+// ac_parse.cu -- kernel K1: FASTA / FASTQ record parser, single pass.
 //
 // Replaces Mash's kseq_read() loop (SURVEY.md section 2.2 stages S1-S2, App. A.2)
 // that runs inside `mash sketch` (auriclass/classes.py:576-596, :696-713).
 // Input: raw inflated text in HBM.  Output: the sanitised compacted base stream Z
 // (kmer_core.cuh): sequence characters only, 0x00 after/between records.
 //
-// Shape: pass A (per 8 KiB tile: newline/line-start ballots as 32-bit masks per
-// thread, what the tile would emit under every incoming parser state) -> a one-CTA
-// scan that threads the parser state (FASTQ line phase / FASTA line type) and the
-// output offsets through the tiles -> pass C (classify again with the known state,
-// compact through shared memory, coalesced byte stores).  A segment (<= 32 MiB)
-// stays L2 resident between the passes, so HBM sees the text once.
+// One kernel, HBM sees the text once.  A CTA takes the next 8 KiB tile (ticket),
+// every thread loads 32 bytes (two coalesced 16-byte loads) and turns them into
+// newline / line-start bit masks.  What a tile emits depends on the parser state at
+// its first byte (FASTQ: line phase 0..3, FASTA: header or sequence line) and on the
+// output offset; both are chained through the tiles with decoupled look-back (one
+// 64-bit status word per tile and quantity, no second pass, no scan kernel):
+//   stage 1  state   FASTQ: sum of newline counts (mod 4)   FASTA: type of the last line start
+//   stage 2  offset  sum of the bytes the earlier tiles emit
+// The emitted byte runs are then compacted through shared memory (word-granular
+// funnel copies), sanitised word-parallel on the way out and written to Z as aligned
+// 16-byte vectors.  The last tile leaves the parser state for the next segment.
 //
 // FASTQ is parsed as strict 4-line records and *verified* (every record starts
 // with '@', its third line with '+', sequence and quality byte totals match, the
@@ -22,9 +27,8 @@ namespace ac {
 
 namespace {
 
-__device__ __forceinline__ uint32_t gather_nib(uint32_t eq) {  // eq: 0xFF per selected byte -> 4-bit mask
-    return ((eq & 0x01010101u) * 0x01020408u) >> 24;
-}
+typedef unsigned long long u64;
+
 __device__ __forceinline__ uint32_t bit_range(int a, int b) {  // bits [a, b), 0 <= a <= b <= 32
     uint32_t hi = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
     uint32_t lo = (a >= 32) ? 0xffffffffu : ((1u << a) - 1u);
@@ -33,7 +37,6 @@ __device__ __forceinline__ uint32_t bit_range(int a, int b) {  // bits [a, b), 0
 
 struct ChunkMasks {
     uint32_t valid, nl;
-    const uint8_t *bytes;  // address of the chunk's byte 0 (line-start characters are read from here, L1 hits)
 };
 
 // 0x80 in every byte of w equal to '\n' (exact: no borrow artefacts)
@@ -68,10 +71,9 @@ __device__ __forceinline__ void load_chunk(const SegDesc &sd, uint32_t tile, uin
 #pragma unroll
     for (int j = 0; j < 8; j++) nl |= (((newline_bits(w[j]) >> 7) * 0x01020408u) >> 24) << (4 * j);
     m.nl = nl & m.valid;
-    m.bytes = sd.base + pos;
 }
 
-// Is the byte just before this thread's first valid byte a newline?  (seg_first: value to use
+// Is the byte just before this thread's first valid byte a newline?  (seg_first_ls: value to use
 // when that byte is the first byte of the segment.)
 __device__ __forceinline__ bool prev_is_newline(const SegDesc &sd, uint32_t tile, const ChunkMasks &m,
                                                 uint32_t seg_first_ls, uint32_t *s_last /*[8]*/) {
@@ -85,6 +87,7 @@ __device__ __forceinline__ bool prev_is_newline(const SegDesc &sd, uint32_t tile
         const long long pos = (long long)tile * K1_TILE + (long long)threadIdx.x * K1_CHUNK;
         const int vlo = __ffs(m.valid) - 1;
         if (pos + vlo == (long long)sd.skip) r = seg_first_ls != 0;          // first byte of the segment
+        else if (vlo > 0) r = false;                                          // cannot happen (valid starts at bit 0 except at the segment start)
         else if (lane > 0) r = up != 0;
         else if (warp > 0) r = s_last[warp - 1] != 0;
         else r = sd.base[pos - 1] == '\n';                                    // peek into the previous tile
@@ -106,144 +109,287 @@ __device__ __forceinline__ uint32_t sanitise4(uint32_t w) {
     const uint32_t vm = (z >> 7) * 0xFFu;
     return (u & vm) | (~vm & 0x01010101u);
 }
+// same, and '\n' (the in-stream marker of a record boundary) -> 0x00
+__device__ __forceinline__ uint32_t sanitise4_sep(uint32_t w) {
+    return sanitise4(w) & ~(newline_bits(w) >> 7);  // newline bytes come out of sanitise4 as 0x01
+}
+
+// ---------------------------------------------------------------- decoupled look-back
+// status word: [63:34] epoch (segment serial of the context, never reused) [33:32] flag [31:0] value
+constexpr uint32_t ST_AGG = 1, ST_INC = 2;
+__device__ __forceinline__ u64 st_pack(uint32_t epoch, uint32_t flag, uint32_t v) {
+    return ((u64)epoch << 34) | ((u64)flag << 32) | v;
+}
+__device__ __forceinline__ u64 ld_status(const u64 *p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(u64 *p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+enum { OP_SUM = 0, OP_LAST = 1 };  // OP_LAST: value bit0 = defined, bit1 = payload; the nearest defined value wins
+
+// Called by one full warp.  Publishes the tile's aggregate, walks back over the earlier tiles until an
+// inclusive prefix is met, publishes the tile's own inclusive prefix, returns the exclusive one.
+// `init` is the exclusive prefix of tile 0 (for OP_LAST it must have bit0 set).
+template <int OP>
+__device__ uint32_t lookback(u64 *st, uint32_t tile, uint32_t epoch, uint32_t agg, uint32_t init) {
+    const int lane = threadIdx.x & 31;
+    uint32_t ex;
+    if (tile == 0) {
+        ex = init;
+    } else {
+        if (lane == 0) st_status(&st[tile], st_pack(epoch, ST_AGG, agg));
+        uint32_t acc = 0;  // OP_SUM: sum of the aggregates walked over so far
+        bool done = false;
+        ex = 0;
+        for (long long base = (long long)tile - 1; !done; base -= 32) {
+            const long long idx = base - lane;
+            uint32_t flag, v;
+            if (idx >= 0) {
+                u64 w;
+                do {
+                    w = ld_status(&st[idx]);
+                    flag = (uint32_t)(w >> 32) & 3u;
+                } while ((uint32_t)(w >> 34) != epoch || flag == 0);
+                v = (uint32_t)w;
+            } else {
+                flag = ST_INC;  // virtual tile -1 carries the initial state
+                v = init;
+            }
+            const unsigned inc_mask = __ballot_sync(FULL, flag == ST_INC);
+            const int first_inc = inc_mask ? (__ffs(inc_mask) - 1) : 32;  // nearest inclusive prefix in this window
+            if (OP == OP_SUM) {
+                uint32_t c = (lane <= first_inc) ? v : 0u;
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(FULL, c, d);
+                acc += c;
+                if (first_inc < 32) { ex = acc; done = true; }
+            } else {
+                const unsigned def_mask = __ballot_sync(FULL, lane <= first_inc && (v & 1u));
+                if (def_mask) { ex = __shfl_sync(FULL, v, __ffs(def_mask) - 1); done = true; }
+                // an inclusive prefix is always defined, so first_inc < 32 implies def_mask != 0
+            }
+        }
+    }
+    uint32_t inc;
+    if (OP == OP_SUM) inc = ex + agg; else inc = (agg & 1u) ? agg : ex;
+    if (lane == 0) st_status(&st[tile], st_pack(epoch, ST_INC, inc));
+    return ex;
+}
+
+// ---------------------------------------------------------------- compaction through shared memory
+constexpr int SW_STRIDE = 9;  // words per thread in s_words (8 + 1 pad: conflict-free column access)
+
+// copy the thread's emitted byte runs (mask em over its 32-byte chunk) to s_out starting at byte d
+__device__ __forceinline__ void compact_runs(const uint32_t *s_words, uint8_t *s_out, uint32_t tid, uint32_t em, uint32_t d) {
+    const uint32_t *src_w = s_words + tid * SW_STRIDE;
+    const uint8_t *src_b = reinterpret_cast<const uint8_t *>(src_w);
+    while (em) {
+        const int a = __ffs(em) - 1;
+        const uint32_t inv = ~em >> a;                 // bit 0 is clear; first set bit = run length
+        const int len = inv ? (__ffs(inv) - 1) : (32 - a);
+        int sa = a, n = len;
+        // head: bytes until the destination is word aligned
+        while (n > 0 && (d & 3u)) { s_out[d++] = src_b[sa++]; n--; }
+        if (n >= 4) {
+            const int sh = (sa & 3) * 8;
+            int wi = sa >> 2;
+            uint32_t lo = src_w[wi];
+            uint32_t *dst = reinterpret_cast<uint32_t *>(s_out + d);
+            const int nw = n >> 2;
+            for (int q = 0; q < nw; q++) {
+                const uint32_t hi = src_w[wi + 1];     // wi + 1 <= 8: the pad word, shifted out when sh == 0
+                dst[q] = __funnelshift_r(lo, hi, sh);
+                lo = hi; wi++;
+            }
+            d += 4 * nw; sa += 4 * nw; n -= 4 * nw;
+        }
+        while (n > 0) { s_out[d++] = src_b[sa++]; n--; }
+        em = (a + len >= 32) ? 0u : (em & ~((1u << (a + len)) - 1u));
+    }
+}
+
+// s_out[s_off .. s_off + cnt) -> Z[out_off ..), sanitised; aligned 16-byte vectors inside, bytes at the edges
+__device__ __forceinline__ void write_out(const uint8_t *s_out, uint32_t s_off, uint32_t cnt, uint8_t *Z, uint32_t out_off) {
+    uint8_t *zal = Z + (out_off - s_off);  // 16-byte aligned: s_off = out_off & 15
+    const uint32_t end = s_off + cnt;
+    const uint32_t nvec = (end + 15) >> 4;
+    for (uint32_t i = threadIdx.x; i < nvec; i += K1_THREADS) {
+        const uint32_t b0 = 16 * i;
+        uint4 v = reinterpret_cast<const uint4 *>(s_out)[i];
+        v.x = sanitise4_sep(v.x); v.y = sanitise4_sep(v.y); v.z = sanitise4_sep(v.z); v.w = sanitise4_sep(v.w);
+        if (b0 >= s_off && b0 + 16 <= end) {
+            reinterpret_cast<uint4 *>(zal)[i] = v;
+        } else {
+            const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const uint32_t b = b0 + j;
+                if (b >= s_off && b < end) zal[b] = (uint8_t)(ww[j >> 2] >> (8 * (j & 3)));
+            }
+        }
+    }
+}
+
+// stream carry: the last Z_CARRY bytes of the previous segment's stream go in front of this one's
+__device__ __forceinline__ void copy_carry(const SegDesc &sd, const ParseState &ps, const uint8_t *Zprev, uint8_t *Z) {
+    if (threadIdx.x < Z_CARRY) {
+        uint8_t c = 0;
+        if (!sd.first_of_stream) c = Zprev[ps.n_zbuf - Z_CARRY + threadIdx.x];
+        Z[threadIdx.x] = c;
+    }
+}
+
+struct TileShared {
+    uint32_t w[33];
+    uint32_t last[8];
+    uint32_t acc[6];
+    uint32_t tile, state_in, out_off;
+};
 
 // ---------------------------------------------------------------- FASTQ
-__global__ void __launch_bounds__(K1_THREADS) k1_fq_pass_a(SegDesc sd, TileSum *__restrict__ sums) {
-    __shared__ uint32_t s_w[33];
-    __shared__ uint32_t s_cnt[4];
-    __shared__ uint32_t s_ends;
-    const uint32_t tile = blockIdx.x, tid = threadIdx.x;
+__global__ void __launch_bounds__(K1_THREADS) k1_fastq(SegDesc sd, JobDev *__restrict__ jd, u64 *__restrict__ st1,
+                                                       u64 *__restrict__ st2, const uint8_t *__restrict__ Zprev,
+                                                       uint8_t *__restrict__ Z) {
+    __shared__ TileShared sh;
+    __shared__ __align__(16) uint32_t s_words[K1_THREADS * SW_STRIDE + 4];
+    __shared__ __align__(16) uint8_t s_out[K1_TILE + 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sh.tile = (uint32_t)(atomicAdd(&jd->tile_ticket, 1u) - sd.ticket_base);
+    if (tid < 6) sh.acc[tid] = 0;
+    __syncthreads();
+    const uint32_t tile = sh.tile;
+    const ParseState ps = jd->ps[sd.serial & 1u];
+    if (tile == 0) copy_carry(sd, ps, Zprev, Z);
+
     uint32_t w[8];
     ChunkMasks m;
     load_chunk(sd, tile, tid, w, m);
-    if (tid < 4) s_cnt[tid] = 0;
-    if (tid == 0) s_ends = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s_words[tid * SW_STRIDE + j] = w[j];
     uint32_t total_nl;
-    const uint32_t L0 = block_excl_sum<K1_THREADS>(__popc(m.nl), s_w, total_nl);
-    uint32_t packed = 0;  // four 8-bit byte counts, index = local line index & 3
+    const uint32_t L0 = block_excl_sum<K1_THREADS>(__popc(m.nl), sh.w, total_nl);
+    const bool prev_nl = prev_is_newline(sd, tile, m, ps.at_line_start, sh.last);
+
+    // one walk over the thread's lines: byte masks per local line index (mod 4) and what the line starts look like
+    uint32_t lm[4] = {0, 0, 0, 0};
+    uint32_t not_at = 0, not_plus = 0;  // bit r: a line with local index r (mod 4) starts here with a byte other than '@' / '+'
+    uint32_t ends = 0;
     if (m.valid) {
         const int vlo = __ffs(m.valid) - 1, vhi = 32 - __clz(m.valid);
+        const uint8_t *bytes = reinterpret_cast<const uint8_t *>(s_words + tid * SW_STRIDE);
         int pos = vlo;
         uint32_t L = L0;
+        bool ls = prev_nl;
         while (true) {
-            const uint32_t r = m.nl & (0xffffffffu << pos);
-            const int end = r ? (__ffs(r) - 1) : (vhi - 1);
-            packed += (uint32_t)(end - pos + 1) << (8 * (L & 3));
-            if (!r || end + 1 >= vhi) break;
-            pos = end + 1; L++;
+            const uint32_t r = L & 3u;
+            if (ls) {
+                const uint8_t ch = bytes[pos];
+                if (ch != '@') not_at |= 1u << r;
+                if (ch != '+') not_plus |= 1u << r;
+            }
+            const uint32_t rest = m.nl & (0xffffffffu << pos);
+            const int end = rest ? (__ffs(rest) - 1) : (vhi - 1);
+            const uint32_t seg = bit_range(pos, end + 1);
+#pragma unroll
+            for (int q = 0; q < 4; q++) if (q == (int)r) lm[q] |= seg;
+            if (!rest || end + 1 >= vhi) break;
+            pos = end + 1; L++; ls = true;
         }
         // does this thread own the last valid byte of the tile?
         const long long pos0 = (long long)tile * K1_TILE + (long long)tid * K1_CHUNK;
         const long long hi = (long long)sd.skip + sd.len;
         const long long tile_hi = min(hi, (long long)(tile + 1) * K1_TILE);
-        if (pos0 + vhi == tile_hi) s_ends = (m.nl >> (vhi - 1)) & 1u;
+        if (pos0 + vhi == tile_hi) ends = 0x80000000u | ((m.nl >> (vhi - 1)) & 1u);
     }
-    // per-counter warp reduction: two 16-bit lanes per shuffle
-    uint32_t lo = (packed & 0xFFu) | (((packed >> 8) & 0xFFu) << 16);
-    uint32_t hi2 = ((packed >> 16) & 0xFFu) | (((packed >> 24) & 0xFFu) << 16);
+    if (ends) sh.acc[4] = ends;
+    {   // tile totals of the four per-line-index byte counts (two 16-bit lanes per shuffle)
+        uint32_t lo = __popc(lm[0]) | (__popc(lm[1]) << 16), hi2 = __popc(lm[2]) | (__popc(lm[3]) << 16);
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        lo += __shfl_xor_sync(FULL, lo, d);
-        hi2 += __shfl_xor_sync(FULL, hi2, d);
-    }
-    if ((tid & 31) == 0) {
-        atomicAdd(&s_cnt[0], lo & 0xFFFFu); atomicAdd(&s_cnt[1], lo >> 16);
-        atomicAdd(&s_cnt[2], hi2 & 0xFFFFu); atomicAdd(&s_cnt[3], hi2 >> 16);
+        for (int d = 16; d >= 1; d >>= 1) {
+            lo += __shfl_xor_sync(FULL, lo, d);
+            hi2 += __shfl_xor_sync(FULL, hi2, d);
+        }
+        if (lane == 0) {
+            atomicAdd(&sh.acc[0], lo & 0xFFFFu); atomicAdd(&sh.acc[1], lo >> 16);
+            atomicAdd(&sh.acc[2], hi2 & 0xFFFFu); atomicAdd(&sh.acc[3], hi2 >> 16);
+        }
     }
     __syncthreads();
-    if (tid == 0) {
-        TileSum s;
-        s.a = total_nl;
-        s.c[0] = s_cnt[0]; s.c[1] = s_cnt[1]; s.c[2] = s_cnt[2]; s.c[3] = s_cnt[3];
-        s.ends_nl = s_ends;
-        sums[tile] = s;
-    }
-}
-
-__global__ void __launch_bounds__(K1_THREADS) k1_fq_pass_c(SegDesc sd, const TileIn *__restrict__ tin,
-                                                           JobDev *__restrict__ jd, uint8_t *__restrict__ Z) {
-    __shared__ uint32_t s_w[33];
-    __shared__ uint32_t s_last[8];
-    __shared__ __align__(16) uint32_t s_words[K1_THREADS * 8];
-    const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const TileIn ti = tin[tile];
-    uint32_t w[8];
-    ChunkMasks m;
-    load_chunk(sd, tile, tid, w, m);
-#pragma unroll
-    for (int v = 0; v < 2; v++)
-        reinterpret_cast<uint4 *>(s_words)[tid * 2 + v] = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
-    uint32_t total_nl;
-    const uint32_t L0 = block_excl_sum<K1_THREADS>(__popc(m.nl), s_w, total_nl);
-    const bool prev_nl = prev_is_newline(sd, tile, m, ti.first_ls, s_last);
-    uint32_t emit = 0, err = 0;
-    if (m.valid) {
-        const int vlo = __ffs(m.valid) - 1, vhi = 32 - __clz(m.valid);
-        int pos = vlo;
-        uint32_t ph = (ti.state + L0) & 3u;
-        bool ls = prev_nl;
-        while (true) {
-            if (ls && !(ph & 1u)) {
-                const uint8_t ch = __ldg(m.bytes + pos);
-                if (ph == 0 && ch != '@') err |= FERR_FQ_HEADER;
-                if (ph == 2 && ch != '+') err |= FERR_FQ_PLUS;
-            }
-            const uint32_t r = m.nl & (0xffffffffu << pos);
-            const int end = r ? (__ffs(r) - 1) : (vhi - 1);
-            if (ph == 1) emit |= bit_range(pos, end + 1);
-            if (!r || end + 1 >= vhi) break;
-            pos = end + 1; ph = (ph + 1) & 3u; ls = true;
+    if (warp == 0) {
+        // stage 1: line phase at the tile's first byte; stage 2: output offset
+        const uint32_t nl_ex = lookback<OP_SUM>(st1, tile, sd.epoch, total_nl, ps.fq_phase);
+        const uint32_t ph = nl_ex & 3u;
+        const uint32_t seq_bytes = sh.acc[(1u - ph) & 3u], qual_bytes = sh.acc[(3u - ph) & 3u];
+        const uint32_t off = lookback<OP_SUM>(st2, tile, sd.epoch, seq_bytes, Z_CARRY);
+        if (lane == 0) {
+            sh.state_in = ph; sh.out_off = off;
+            if (seq_bytes) atomicAdd(&jd->fq_seq_bytes, (u64)seq_bytes);
+            if (qual_bytes) atomicAdd(&jd->fq_qual_bytes, (u64)qual_bytes);
         }
     }
+    __syncthreads();
+    const uint32_t ph = sh.state_in, out_off = sh.out_off;
+    const uint32_t r_seq = (1u - ph) & 3u, r_hdr = (0u - ph) & 3u, r_plus = (2u - ph) & 3u;
+    uint32_t emit = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) if (q == (int)r_seq) emit = lm[q];
+    uint32_t err = 0;
+    if ((not_at >> r_hdr) & 1u) err |= FERR_FQ_HEADER;
+    if ((not_plus >> r_plus) & 1u) err |= FERR_FQ_PLUS;
     if (err) atomicOr(&jd->format_error, err);
     uint32_t total_emit;
-    const uint32_t E = block_excl_sum<K1_THREADS>(__popc(emit), s_w, total_emit);  // also orders s_words
-    // flat copy: a warp walks its own 1 KiB region 128 bytes at a time
-#pragma unroll 1
-    for (int step = 0; step < 8; step++) {
-        const int srcl = 4 * step + (lane >> 3);
-        const uint32_t em = __shfl_sync(FULL, emit, srcl);
-        const uint32_t e0 = __shfl_sync(FULL, E, srcl);
-        const int bitoff = (lane & 7) * 4;
-        const uint32_t nib = (em >> bitoff) & 0xFu;
-        if (nib) {
-            const uint32_t word = s_words[warp * 256 + step * 32 + lane];
-            uint32_t sw = sanitise4(word) & ~((newline_bits(word) >> 7) * 0xFFu);  // newline -> record separator
-            uint32_t off = ti.out_off + e0 + __popc(em & ((1u << bitoff) - 1u));
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if ((nib >> k) & 1u) Z[off++] = (uint8_t)(sw >> (8 * k));
+    const uint32_t E = block_excl_sum<K1_THREADS>(__popc(emit), sh.w, total_emit);  // also orders s_words
+    const uint32_t s_off = out_off & 15u;
+    compact_runs(s_words, s_out, tid, emit, s_off + E);
+    __syncthreads();
+    write_out(s_out, s_off, total_emit, Z, out_off);
+
+    if (tile + 1 == sd.n_tiles && tid == 0) {  // last tile: parser state for the next segment / file
+        const uint32_t end_state = (ph + total_nl) & 3u;
+        const uint32_t ends_nl = (sh.acc[4] & 0x80000000u) ? (sh.acc[4] & 1u) : ps.at_line_start;
+        ParseState nx;
+        nx.n_zbuf = out_off + total_emit;
+        if (sd.last_of_file) {
+            if (end_state != 0 || !ends_nl) atomicOr(&jd->format_error, (uint32_t)FERR_FQ_TRUNC);
+            nx.fq_phase = 0; nx.fa_type = 0; nx.at_line_start = 1;
+        } else {
+            nx.fq_phase = end_state; nx.fa_type = ps.fa_type; nx.at_line_start = ends_nl;
         }
+        jd->ps[(sd.serial + 1u) & 1u] = nx;
     }
 }
 
 // ---------------------------------------------------------------- FASTA
-// classification shared by pass A and pass C
 struct FaThread {
-    uint32_t emit, sepm;      // pass C masks
-    uint32_t head_emit, rest_emit;
+    uint32_t emit;       // bytes emitted whatever the incoming line type (lines that start inside the chunk, and
+                         // the chunk's head when its type is known from an earlier line start of the tile)
+    uint32_t head;       // bytes of the chunk's head line, emitted iff the incoming type is "sequence"
+    uint32_t sepm;       // header line starts ('>' / '@'): emitted as a record separator
     uint32_t err;
 };
 
-template <bool PASS_C>
-__device__ __forceinline__ FaThread fa_classify(const ChunkMasks &m, uint32_t lsm, bool known, uint32_t type) {
-    FaThread o{0, 0, 0, 0, 0};
+__device__ __forceinline__ FaThread fa_classify(const ChunkMasks &m, uint32_t lsm, const uint8_t *bytes, bool known, uint32_t type) {
+    FaThread o{0, 0, 0, 0};
     if (!m.valid) return o;
     const int vlo = __ffs(m.valid) - 1, vhi = 32 - __clz(m.valid);
     int pos = vlo;
     while (true) {
         if ((lsm >> pos) & 1u) {
-            const uint8_t ch = __ldg(m.bytes + pos);
+            const uint8_t ch = bytes[pos];
             type = (ch == '>' || ch == '@') ? 0u : 1u;
             known = true;
             if (ch == '+') o.err |= FERR_FA_PLUS;
-            if (type == 0u) { o.rest_emit += 1; if (PASS_C) { o.emit |= 1u << pos; o.sepm |= 1u << pos; } }
+            if (type == 0u) { o.emit |= 1u << pos; o.sepm |= 1u << pos; }
         }
         const uint32_t next = (pos + 1 < 32) ? (lsm & (0xffffffffu << (pos + 1))) : 0u;
         const int end = next ? (__ffs(next) - 1) : vhi;  // exclusive
         const uint32_t body = bit_range(pos, end) & ~m.nl & m.valid;
-        if (!known) o.head_emit += __popc(body);
-        else if (type == 1u) { o.rest_emit += __popc(body); if (PASS_C) o.emit |= body; }
+        if (!known) o.head |= body;
+        else if (type == 1u) o.emit |= body;
         if (!next) break;
         pos = end;
     }
@@ -256,221 +402,104 @@ __device__ __forceinline__ uint32_t fa_line_starts(const ChunkMasks &m, bool pre
     return ((m.nl << 1) | (prev_nl ? (1u << vlo) : 0u)) & m.valid;
 }
 
-__global__ void __launch_bounds__(K1_THREADS) k1_fa_pass_a(SegDesc sd, const JobDev *__restrict__ jd,
-                                                           TileSum *__restrict__ sums) {
-    __shared__ uint32_t s_w[33];
-    __shared__ uint32_t s_last[8];
-    __shared__ uint32_t s_acc[3];  // head, rest, ends
-    const uint32_t tile = blockIdx.x, tid = threadIdx.x;
+__global__ void __launch_bounds__(K1_THREADS) k1_fasta(SegDesc sd, JobDev *__restrict__ jd, u64 *__restrict__ st1,
+                                                       u64 *__restrict__ st2, const uint8_t *__restrict__ Zprev,
+                                                       uint8_t *__restrict__ Z) {
+    __shared__ TileShared sh;
+    __shared__ __align__(16) uint32_t s_words[K1_THREADS * SW_STRIDE + 4];
+    __shared__ __align__(16) uint8_t s_out[K1_TILE + 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sh.tile = (uint32_t)(atomicAdd(&jd->tile_ticket, 1u) - sd.ticket_base);
+    if (tid < 6) sh.acc[tid] = 0;
+    __syncthreads();
+    const uint32_t tile = sh.tile;
+    const ParseState ps = jd->ps[sd.serial & 1u];
+    if (tile == 0) copy_carry(sd, ps, Zprev, Z);
+
     uint32_t w[8];
     ChunkMasks m;
     load_chunk(sd, tile, tid, w, m);
-    if (tid < 3) s_acc[tid] = 0;
-    const bool prev_nl = prev_is_newline(sd, tile, m, jd->at_line_start, s_last);
+#pragma unroll
+    for (int j = 0; j < 8; j++) s_words[tid * SW_STRIDE + j] = w[j];
+    const bool prev_nl = prev_is_newline(sd, tile, m, ps.at_line_start, sh.last);
     const uint32_t lsm = fa_line_starts(m, prev_nl);
-    uint32_t enc = 0;
+    uint8_t *bytes = reinterpret_cast<uint8_t *>(s_words + tid * SW_STRIDE);
+    uint32_t enc = 0;  // (thread + 1) << 1 | type of the thread's last line start
     if (lsm) {
-        const uint8_t ch = __ldg(m.bytes + (31 - __clz(lsm)));
+        const uint8_t ch = bytes[31 - __clz(lsm)];
         enc = ((tid + 1u) << 1) | ((ch == '>' || ch == '@') ? 0u : 1u);
     }
-    const uint32_t inc = block_incl_max<K1_THREADS>(enc, s_w);
-    // exclusive value = inclusive value of the previous thread
-    uint32_t prev = __shfl_up_sync(FULL, inc, 1);
-    if ((tid & 31) == 31) s_last[tid >> 5] = inc;
+    const uint32_t inc = block_incl_max<K1_THREADS>(enc, sh.w);
+    uint32_t prev = __shfl_up_sync(FULL, inc, 1);  // exclusive value = inclusive value of the previous thread
+    if (lane == 31) sh.last[warp] = inc;
     __syncthreads();
-    if ((tid & 31) == 0) prev = (tid >> 5) ? s_last[(tid >> 5) - 1] : 0u;
-    FaThread o = fa_classify<false>(m, lsm, prev != 0, prev & 1u);
-    uint32_t h = o.head_emit, r = o.rest_emit;
+    if (lane == 0) prev = warp ? sh.last[warp - 1] : 0u;
+    const FaThread o = fa_classify(m, lsm, bytes, prev != 0, prev & 1u);
+    if (o.err) atomicOr(&jd->format_error, o.err);
+    {
+        uint32_t h = __popc(o.head), r = __popc(o.emit);
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        h += __shfl_xor_sync(FULL, h, d);
-        r += __shfl_xor_sync(FULL, r, d);
+        for (int d = 16; d >= 1; d >>= 1) {
+            h += __shfl_xor_sync(FULL, h, d);
+            r += __shfl_xor_sync(FULL, r, d);
+        }
+        if (lane == 0) { atomicAdd(&sh.acc[0], h); atomicAdd(&sh.acc[1], r); }
     }
-    if ((tid & 31) == 0) { atomicAdd(&s_acc[0], h); atomicAdd(&s_acc[1], r); }
     if (m.valid) {
         const int vhi = 32 - __clz(m.valid);
         const long long pos0 = (long long)tile * K1_TILE + (long long)tid * K1_CHUNK;
         const long long hi = (long long)sd.skip + sd.len;
         const long long tile_hi = min(hi, (long long)(tile + 1) * K1_TILE);
-        if (pos0 + vhi == tile_hi) s_acc[2] = (m.nl >> (vhi - 1)) & 1u;
+        if (pos0 + vhi == tile_hi) sh.acc[4] = 0x80000000u | ((m.nl >> (vhi - 1)) & 1u);
+    }
+    if (tid == K1_THREADS - 1) sh.acc[5] = inc;  // tile's last line start (0: none)
+    // header line starts become the record separator: mark them with '\n' in the staged text
+    for (uint32_t sp = o.sepm; sp; sp &= sp - 1) bytes[__ffs(sp) - 1] = '\n';
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t last = sh.acc[5];
+        const uint32_t agg = last ? (1u | ((last & 1u) << 1)) : 0u;
+        const uint32_t ty_ex = lookback<OP_LAST>(st1, tile, sd.epoch, agg, 1u | (ps.fa_type << 1));
+        const uint32_t ty = (ty_ex >> 1) & 1u;
+        const uint32_t out_bytes = sh.acc[1] + (ty ? sh.acc[0] : 0u);
+        const uint32_t off = lookback<OP_SUM>(st2, tile, sd.epoch, out_bytes, Z_CARRY);
+        if (lane == 0) { sh.state_in = ty; sh.out_off = off; }
     }
     __syncthreads();
-    if (tid == K1_THREADS - 1) {
-        TileSum s;
-        s.a = (inc != 0 ? 1u : 0u) | ((inc & 1u) << 1);
-        s.c[0] = s_acc[0]; s.c[1] = s_acc[1]; s.c[2] = 0; s.c[3] = 0;
-        s.ends_nl = s_acc[2];
-        sums[tile] = s;
-    }
-}
-
-__global__ void __launch_bounds__(K1_THREADS) k1_fa_pass_c(SegDesc sd, const TileIn *__restrict__ tin,
-                                                           JobDev *__restrict__ jd, uint8_t *__restrict__ Z) {
-    __shared__ uint32_t s_w[33];
-    __shared__ uint32_t s_last[8];
-    __shared__ __align__(16) uint32_t s_words[K1_THREADS * 8];
-    const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const TileIn ti = tin[tile];
-    uint32_t w[8];
-    ChunkMasks m;
-    load_chunk(sd, tile, tid, w, m);
-#pragma unroll
-    for (int v = 0; v < 2; v++)
-        reinterpret_cast<uint4 *>(s_words)[tid * 2 + v] = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
-    const bool prev_nl = prev_is_newline(sd, tile, m, ti.first_ls, s_last);
-    const uint32_t lsm = fa_line_starts(m, prev_nl);
-    uint32_t enc = 0;
-    if (lsm) {
-        const uint8_t ch = __ldg(m.bytes + (31 - __clz(lsm)));
-        enc = ((tid + 1u) << 1) | ((ch == '>' || ch == '@') ? 0u : 1u);
-    }
-    const uint32_t inc = block_incl_max<K1_THREADS>(enc, s_w);
-    uint32_t prev = __shfl_up_sync(FULL, inc, 1);
-    if (lane == 31) s_last[warp] = inc;
-    __syncthreads();
-    if (lane == 0) prev = warp ? s_last[warp - 1] : 0u;
-    const uint32_t type_in = prev ? (prev & 1u) : ti.state;
-    FaThread o = fa_classify<true>(m, lsm, true, type_in);
-    if (o.err) atomicOr(&jd->format_error, o.err);
+    const uint32_t ty = sh.state_in, out_off = sh.out_off;
+    const uint32_t emit = o.emit | (ty ? o.head : 0u);
     uint32_t total_emit;
-    const uint32_t E = block_excl_sum<K1_THREADS>(__popc(o.emit), s_w, total_emit);
-#pragma unroll 1
-    for (int step = 0; step < 8; step++) {
-        const int srcl = 4 * step + (lane >> 3);
-        const uint32_t em = __shfl_sync(FULL, o.emit, srcl);
-        const uint32_t sp = __shfl_sync(FULL, o.sepm, srcl);
-        const uint32_t e0 = __shfl_sync(FULL, E, srcl);
-        const int bitoff = (lane & 7) * 4;
-        const uint32_t nib = (em >> bitoff) & 0xFu;
-        if (nib) {
-            const uint32_t word = s_words[warp * 256 + step * 32 + lane];
-            const uint32_t spn = (sp >> bitoff) & 0xFu;
-            // separator bytes -> 0x00: expand the 4-bit mask to a byte mask
-            const uint32_t spm = ((spn & 1u) * 0xFFu) | (((spn >> 1) & 1u) * 0xFF00u) | (((spn >> 2) & 1u) * 0xFF0000u) |
-                                 (((spn >> 3) & 1u) * 0xFF000000u);
-            const uint32_t sw = sanitise4(word) & ~spm;
-            uint32_t off = ti.out_off + e0 + __popc(em & ((1u << bitoff) - 1u));
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if ((nib >> k) & 1u) Z[off++] = (uint8_t)(sw >> (8 * k));
-        }
-    }
-}
-
-// ---------------------------------------------------------------- scan
-constexpr int SCAN_T = 1024;
-
-__global__ void __launch_bounds__(SCAN_T) k1_scan(SegDesc sd, const TileSum *__restrict__ sums,
-                                                  TileIn *__restrict__ tin, JobDev *__restrict__ jd,
-                                                  uint8_t *__restrict__ Z) {
-    __shared__ uint32_t s_w[33];
-    const uint32_t tid = threadIdx.x;
-    const uint32_t n = sd.n_tiles;
-    const uint32_t per = (n + SCAN_T - 1) / SCAN_T;
-    const uint32_t t0 = min(n, tid * per), t1 = min(n, t0 + per);
-
-    // carry: last Z_CARRY bytes of the previous segment's stream move to the front
-    const uint32_t old_n = jd->n_zbuf;
-    uint8_t carry = 0;
-    if (tid < Z_CARRY && !sd.first_of_stream) carry = Z[old_n - Z_CARRY + tid];
-    const uint32_t phase0 = jd->fq_phase, type0 = jd->fa_type, ls0 = jd->at_line_start;
+    const uint32_t E = block_excl_sum<K1_THREADS>(__popc(emit), sh.w, total_emit);
+    const uint32_t s_off = out_off & 15u;
+    compact_runs(s_words, s_out, tid, emit, s_off + E);
     __syncthreads();
-    if (tid < Z_CARRY) Z[tid] = carry;
+    write_out(s_out, s_off, total_emit, Z, out_off);
 
-    uint32_t total_out = 0, end_state = 0;
-    if (sd.fmt == FMT_FASTQ) {
-        uint32_t nl_local = 0;
-        for (uint32_t t = t0; t < t1; t++) nl_local += sums[t].a;
-        uint32_t total_nl;
-        uint32_t ex_nl = block_excl_sum<SCAN_T>(nl_local, s_w, total_nl);
-        uint32_t out_local = 0, qual_local = 0, run = ex_nl;
-        for (uint32_t t = t0; t < t1; t++) {
-            const uint32_t ph = (phase0 + run) & 3u;
-            out_local += sums[t].c[(1u - ph) & 3u];
-            qual_local += sums[t].c[(3u - ph) & 3u];
-            run += sums[t].a;
-        }
-        uint32_t total_qual;
-        const uint32_t ex_q = block_excl_sum<SCAN_T>(qual_local, s_w, total_qual);
-        (void)ex_q;
-        uint32_t off = block_excl_sum<SCAN_T>(out_local, s_w, total_out);
-        run = ex_nl;
-        for (uint32_t t = t0; t < t1; t++) {
-            const uint32_t ph = (phase0 + run) & 3u;
-            TileIn ti;
-            ti.state = ph; ti.out_off = Z_CARRY + off; ti.first_ls = (t == 0) ? ls0 : 0u;
-            tin[t] = ti;
-            off += sums[t].c[(1u - ph) & 3u];
-            run += sums[t].a;
-        }
-        end_state = (phase0 + total_nl) & 3u;
-        if (tid == 0) {
-            jd->fq_seq_bytes += total_out;
-            jd->fq_qual_bytes += total_qual;
-        }
-    } else {
-        // incoming line type per tile = type of the nearest earlier tile that saw a line start
-        uint32_t enc = 0;
-        for (uint32_t t = t0; t < t1; t++)
-            if (sums[t].a & 1u) enc = ((t + 1u) << 1) | ((sums[t].a >> 1) & 1u);
-        const uint32_t inc = block_incl_max<SCAN_T>(enc, s_w);
-        // exclusive: value of the previous thread
-        __shared__ uint32_t s_inc[SCAN_T];
-        s_inc[tid] = inc;
-        __syncthreads();
-        uint32_t cur = tid ? s_inc[tid - 1] : 0u;
-        uint32_t out_local = 0;
-        uint32_t c2 = cur;
-        for (uint32_t t = t0; t < t1; t++) {
-            const uint32_t ty = c2 ? (c2 & 1u) : type0;
-            out_local += sums[t].c[1] + (ty ? sums[t].c[0] : 0u);
-            if (sums[t].a & 1u) c2 = ((t + 1u) << 1) | ((sums[t].a >> 1) & 1u);
-        }
-        uint32_t off = block_excl_sum<SCAN_T>(out_local, s_w, total_out);
-        c2 = cur;
-        for (uint32_t t = t0; t < t1; t++) {
-            const uint32_t ty = c2 ? (c2 & 1u) : type0;
-            TileIn ti;
-            ti.state = ty; ti.out_off = Z_CARRY + off; ti.first_ls = (t == 0) ? ls0 : 0u;
-            tin[t] = ti;
-            off += sums[t].c[1] + (ty ? sums[t].c[0] : 0u);
-            if (sums[t].a & 1u) c2 = ((t + 1u) << 1) | ((sums[t].a >> 1) & 1u);
-        }
-        const uint32_t last = s_inc[SCAN_T - 1];
-        end_state = last ? (last & 1u) : type0;
-    }
-    if (tid == 0) {
-        uint32_t nz = Z_CARRY + total_out;
-        const uint32_t ends_nl = n ? sums[n - 1].ends_nl : ls0;
+    if (tile + 1 == sd.n_tiles && tid == 0) {
+        const uint32_t last = sh.acc[5];
+        const uint32_t end_state = last ? (last & 1u) : ty;
+        const uint32_t ends_nl = (sh.acc[4] & 0x80000000u) ? (sh.acc[4] & 1u) : ps.at_line_start;
+        ParseState nx;
+        uint32_t nz = out_off + total_emit;
         if (sd.last_of_file) {
-            if (sd.fmt == FMT_FASTA) Z[nz++] = 0;  // terminate the last record
-            else if (end_state != 0 || !ends_nl || jd->fq_seq_bytes != jd->fq_qual_bytes)
-                atomicOr(&jd->format_error, (uint32_t)FERR_FQ_TRUNC);
-            jd->fq_phase = 0; jd->fa_type = 0; jd->at_line_start = 1;
+            Z[nz++] = 0;  // terminate the last record (this CTA's own stores precede it in program order)
+            nx.fq_phase = 0; nx.fa_type = 0; nx.at_line_start = 1;
         } else {
-            if (sd.fmt == FMT_FASTQ) jd->fq_phase = end_state; else jd->fa_type = end_state;
-            jd->at_line_start = ends_nl;
+            nx.fq_phase = ps.fq_phase; nx.fa_type = end_state; nx.at_line_start = ends_nl;
         }
-        jd->n_zbuf = nz;
+        nx.n_zbuf = nz;
+        jd->ps[(sd.serial + 1u) & 1u] = nx;
     }
 }
 
 }  // namespace
 
-void launch_parse_segment(const LaunchCtx &lc, const SegDesc &sd, TileSum *sums, TileIn *tin, JobDev *jd,
-                          uint8_t *Z) {
-    if (sd.n_tiles) {
-        if (sd.fmt == FMT_FASTQ) k1_fq_pass_a<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, sums);
-        else k1_fa_pass_a<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, jd, sums);
-        ++*lc.launches;
-    }
-    k1_scan<<<1, SCAN_T, 0, lc.stream>>>(sd, sums, tin, jd, Z);
+void launch_parse_segment(const LaunchCtx &lc, const SegDesc &sd, unsigned long long *st1, unsigned long long *st2,
+                          JobDev *jd, const uint8_t *Zprev, uint8_t *Z) {
+    // sd.n_tiles >= 1 (an empty segment still threads the parser state through its single tile)
+    if (sd.fmt == FMT_FASTQ) k1_fastq<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, jd, st1, st2, Zprev, Z);
+    else k1_fasta<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, jd, st1, st2, Zprev, Z);
     ++*lc.launches;
-    if (sd.n_tiles) {
-        if (sd.fmt == FMT_FASTQ) k1_fq_pass_c<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, tin, jd, Z);
-        else k1_fa_pass_c<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, tin, jd, Z);
-        ++*lc.launches;
-    }
 }
 
 }  // namespace ac
