@@ -13,7 +13,13 @@ constexpr int K1_TILE = K1_THREADS * K1_CHUNK;       // 8 KiB of raw text per pa
 constexpr int Z_CARRY = 32;                          // bytes of the base stream carried between segments (>= k-1)
 constexpr size_t SEG_BYTES = 128u << 20;             // raw text per segment: ~13 waves of K2 CTAs, few dependent launches
 constexpr size_t SEG_SAFE_BYTES = 32u << 20;         // segment size when every window may be a candidate (tau = max / safe mode)
-constexpr int K2_THREADS = 256;                      // hash CTA
+#ifndef AC_K2_THREADS
+#define AC_K2_THREADS 256
+#endif
+#ifndef AC_K2_MINB
+#define AC_K2_MINB 4
+#endif
+constexpr int K2_THREADS = AC_K2_THREADS;             // hash CTA
 constexpr int K2_W = 32;                             // window starts per hash thread
 constexpr int K2_TILE = K2_THREADS * K2_W;           // window starts per hash CTA
 constexpr int K2_STAGE = 1024;                       // candidate staging slots per hash CTA (shared memory)

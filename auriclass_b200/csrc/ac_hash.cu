@@ -7,12 +7,16 @@
 //
 // One CTA owns K2_TILE consecutive window starts.  The tile (+64 bytes of halo) is
 // brought into shared memory by one TMA bulk copy (cp.async.bulk + mbarrier); the
-// CTA then builds, once, the reverse complement of the whole tile and per-32-byte
-// validity / separator bitmaps.  A thread owns K2_W consecutive windows and walks
-// them in groups of 8: the k-mer's ASCII words MurmurHash3 needs are byte-granular
-// slices (one PRMT per word) of the forward / reverse-complement words it loads from
-// shared memory -- no rolling state, no 2-bit <-> ASCII expansion.  The group loop
-// keeps the unrolled body ~16 KB so it stays in the instruction cache.
+// CTA then builds, once, the reverse complement of the whole tile, per-32-byte
+// validity / separator bitmaps, the bitmap of valid window starts, and from it the
+// list of *groups*: every maximal run of valid windows is cut into pieces of 32, so
+// lanes are only spent where there is a k-mer to hash (97 % of the slots for 150 bp
+// reads instead of 82 % with a fixed assignment; gaps of any length cost nothing).
+// A quad of lanes takes a group: lane c hashes windows g+c, g+c+4, ... (stride 4 bytes),
+// so one byte alignment of the 15 words it loads per strand (funnel shifts) makes
+// every key word of its 8 windows a whole register -- no per-window byte slicing, no
+// rolling state, no 2-bit <-> ASCII expansion.  The unrolled 8-window body stays in
+// the instruction cache.
 // Integer-issue bound: ~46 IMAD + ~46 LOP3/SHF/IADD3 per k-mer for the hash alone,
 // ~1 byte of HBM/L2 read per k-mer.
 // Hashes <= tau (device-resident, monotonically shrinking) are staged in shared
@@ -41,6 +45,7 @@ __device__ __noinline__ void cand_append_global(unsigned long long h, unsigned l
 template <bool USE64>
 struct CandSink {
     unsigned long long tau;
+    uint32_t tau_top;              // high word of tau (64-bit hashes) / tau itself (32-bit hashes)
     unsigned long long *s_buf;
     uint32_t *s_cnt;
     unsigned long long *cand;
@@ -48,9 +53,11 @@ struct CandSink {
     unsigned long long cand_cap;
     uint32_t *overflow;
     __device__ __forceinline__ void operator()(uint32_t vbits, uint32_t bit, uint64_t h1) {
-        const unsigned long long h = USE64 ? h1 : (h1 & 0xffffffffULL);  // Mash: 32-bit hashes for k <= 16
-        if (h <= tau) {                // rare: tau is a small fraction of the hash space
-            if (vbits & bit) {         // windows touching an invalid byte are dropped here
+        // first look at the high word only (one compare for the common reject); 32-bit mode keeps the low word
+        const uint32_t top = USE64 ? (uint32_t)(h1 >> 32) : (uint32_t)h1;
+        if (top <= tau_top) {              // rare: tau is a small fraction of the hash space
+            const unsigned long long h = USE64 ? h1 : (h1 & 0xffffffffULL);  // Mash: 32-bit hashes for k <= 16
+            if (h <= tau && (vbits & bit)) {   // windows touching an invalid byte are dropped here
                 const uint32_t idx = atomicAdd(s_cnt, 1u);
                 if (idx < (uint32_t)K2_STAGE) s_buf[idx] = h;
                 else cand_append_global(h, cand, cand_count, cand_cap, overflow);
@@ -78,17 +85,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!ok);
 }
 
-constexpr int K2_G = 8;                         // windows per unrolled group (keeps the loop body ~16 KB: fits the I-cache)
 constexpr int K2_TB = K2_TILE + 64;             // tile bytes staged in shared memory (window halo + statistics look-back)
+constexpr int K2_NWV = K2_TILE / 32;            // words of the valid-window bitmap
+// group list capacity: two runs are at least K invalid windows apart, a run of L windows makes ceil(L/32) groups
+template <int K> struct K2MaxGroups { static constexpr int value = K2_TILE / (K + 1) + K2_TILE / 32 + 8; };
 
 template <int K>
-__global__ void __launch_bounds__(K2_THREADS, 4) k2_hash(const uint8_t *__restrict__ Z, JobDev *__restrict__ jd,
+__global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t *__restrict__ Z, JobDev *__restrict__ jd,
                                                          unsigned long long *__restrict__ cand,
                                                          unsigned long long cand_cap, uint32_t seed, int ps_slot) {
+    using Q = ackmer::QuadCfg<K>;
     __shared__ __align__(128) uint8_t s_fwd[K2_TB + 64];  // base stream bytes of the tile (TMA destination)
     __shared__ __align__(16) uint8_t s_rc[K2_TB + 64];    // reverse complement of the tile: s_rc[p'] = comp(s_fwd[TB-1-p'])
     __shared__ uint32_t s_valid[K2_TB / 32 + 2];          // bit b of word c: byte 32c+b is a valid base
     __shared__ uint32_t s_sep[K2_TB / 32 + 2];            // ... is a record separator
+    __shared__ uint32_t s_wv[K2_NWV + 1];                 // bit b of word c: a k-mer to hash starts at byte 32c+b ([K2_NWV] = 0)
+    constexpr int K2_MAXG = K2MaxGroups<K>::value;
+    __shared__ uint16_t s_groups[K2_MAXG];                // start positions of the groups of <= 32 consecutive valid windows
+    __shared__ uint32_t s_ngroups;
+    __shared__ uint32_t s_scan[33];
     __shared__ unsigned long long s_buf[K2_STAGE];
     __shared__ uint32_t s_cnt;
     __shared__ unsigned long long s_base;
@@ -101,9 +116,9 @@ __global__ void __launch_bounds__(K2_THREADS, 4) k2_hash(const uint8_t *__restri
     // a tile is needed while it holds window starts; record-end positions p = start + K < n_zbuf
     // always belong to such a tile (p - K <= n_win - 2)
     if (tile_start >= n_win) return;
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        s_cnt = 0;
+        s_cnt = 0; s_ngroups = 0; s_wv[K2_NWV] = 0;
         mbar_init(&s_bar, 1);
     }
     if (tid < 5) s_stat[tid] = 0;
@@ -131,42 +146,83 @@ __global__ void __launch_bounds__(K2_THREADS, 4) k2_hash(const uint8_t *__restri
     }
     __syncthreads();
 
+    // ---- valid-window bitmap: thread t owns window starts 32t .. 32t+31 of the tile
     const long long run_start = tile_start + (long long)tid * K2_W;
-    // windows of this thread allowed by the stream range: first unprocessed start is
-    // Z_CARRY-(K-1) (earlier ones were hashed with the previous segment), last is n_win-1
+    // windows allowed by the stream range: first unprocessed start is Z_CARRY-(K-1) (earlier ones were
+    // hashed with the previous segment), last is n_win-1
     long long wlo = (long long)(Z_CARRY - (K - 1)) - run_start, whi = n_win - run_start;
     wlo = wlo < 0 ? 0 : wlo; whi = whi > K2_W ? K2_W : whi;
     uint32_t win_ok = 0;
     if (whi > wlo) win_ok = (whi >= 32 ? 0xffffffffu : ((1u << whi) - 1u)) & ~((1u << wlo) - 1u);
     const uint64_t vm64 = (uint64_t)s_valid[tid] | ((uint64_t)s_valid[tid + 1] << 32);
     const uint32_t vmask = (uint32_t)ackmer::windows_all_valid<K>(vm64) & win_ok;
+    s_wv[tid] = vmask;
+
+    // ---- group list.  Runs of valid windows are cut every 32 windows counted from the run's start, so a
+    // run continuing from the previous word puts a cut at bit (its start position mod 32) of this word.
+    {
+        const uint32_t prev_last = __shfl_up_sync(FULL, vmask >> 31, 1);
+        if (lane == 31) s_scan[warp] = vmask >> 31;   // (block_incl_max below syncs before s_scan is reused)
+        __syncthreads();
+        const bool cont = (vmask & 1u) && (lane ? prev_last : (warp ? s_scan[warp - 1] : 0u));  // tile start = fresh run
+        __syncthreads();
+        const uint32_t starts = vmask & ~((vmask << 1) | (cont ? 1u : 0u));
+        // start bit of the run that reaches the end of this word (0 = this word passes an older run through / no run)
+        uint32_t enc = 0;
+        if ((vmask >> 31) && starts) enc = ((tid + 1u) << 5) | (31u - __clz(starts));
+        const uint32_t inc = block_incl_max<K2_THREADS>(enc, s_scan);
+        uint32_t before = __shfl_up_sync(FULL, inc, 1);
+        if (lane == 31) s_scan[warp] = inc;
+        __syncthreads();
+        if (lane == 0) before = warp ? s_scan[warp - 1] : 0u;
+        uint32_t extra = 0xffffffffu;                  // cut of the continuing run inside this word, if any
+        if (cont) {
+            const uint32_t phi = before & 31u;         // before != 0: the run started at some word's start bit
+            const uint32_t ones = (vmask == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~vmask) - 1);
+            if (phi < ones && phi != 0u) extra = phi;  // phi == 0: the run started at bit 0 of a word, its cut is bit 0 here
+            else if (phi == 0u) extra = 0u;
+        }
+        const uint32_t n_mine = __popc(starts) + (extra != 0xffffffffu ? 1u : 0u);
+        if (n_mine) {
+            uint32_t slot = atomicAdd(&s_ngroups, n_mine);
+            if (extra != 0xffffffffu) { if (slot < K2_MAXG) s_groups[slot] = (uint16_t)(32u * tid + extra); slot++; }
+            for (uint32_t st = starts; st; st &= st - 1, slot++)
+                if (slot < K2_MAXG) s_groups[slot] = (uint16_t)(32u * tid + (uint32_t)(__ffs(st) - 1));
+        }
+    }
+    __syncthreads();
+    const uint32_t n_groups = s_ngroups;
+    if (n_groups > (uint32_t)K2_MAXG) __trap();  // cannot happen (see K2MaxGroups)
 
     CandSink<(K > 16)> sink;
     sink.tau = jd->tau;
+    sink.tau_top = (K > 16) ? (uint32_t)(sink.tau >> 32) : (uint32_t)sink.tau;
     sink.s_buf = s_buf; sink.s_cnt = &s_cnt;
     sink.cand = cand; sink.cand_count = &jd->cand_count; sink.cand_cap = cand_cap;
     sink.overflow = &jd->overflow;
 
-    if (__any_sync(FULL, vmask != 0)) {
-        // forward words of group g start at byte 32*tid + 8*g; reverse-complement window i of the
-        // group starts at byte RCB - 32*tid - 8*g - i with RCB = TB - K; both word-aligned up to a
-        // compile-time byte offset
-        constexpr int NF = (K2_G - 1 + K + 3) / 4;                 // forward words per group
-        constexpr int RC_LOW = K2_TB - K - (K2_G - 1);             // byte where window G-1 of (tid 0, g 0) starts
-        constexpr int RC_WORD = RC_LOW >> 2;                       // its word
-        constexpr int RC_PAR = RC_WORD & 1;                        // keep 8-byte aligned loads
-        constexpr int RC_OFF = (RC_LOW & 3) + 4 * RC_PAR;          // byte offset of window G-1 inside the loaded words
-        constexpr int NR = (RC_OFF + (K2_G - 1) + K + 3) / 4;      // reverse words per group
-        const uint2 *pf = reinterpret_cast<const uint2 *>(s_fwd) + 4 * tid;
-        const uint2 *pr = reinterpret_cast<const uint2 *>(s_rc) + ((RC_WORD - RC_PAR) >> 1) - 4 * tid;
+    // ---- hash: a quad per group, lane c takes windows g+c+4j
+    {
+        const uint32_t quad = lane >> 2, c = lane & 3u;
+        const uint32_t *fwd_w = reinterpret_cast<const uint32_t *>(s_fwd);
+        const uint32_t *rc_w = reinterpret_cast<const uint32_t *>(s_rc);
 #pragma unroll 1
-        for (int g = 0; g < K2_W / K2_G; g++) {
-            uint32_t fw[2 * ((NF + 1) / 2)], rw[2 * ((NR + 1) / 2)];
+        for (uint32_t gi = warp * 8u + quad; gi < n_groups; gi += (K2_THREADS / 32) * 8u) {
+            const uint32_t g = s_groups[gi];
+            // the 32 windows from g on, restricted to the run that starts at g (a later run has its own group)
+            uint32_t vb = __funnelshift_r(s_wv[g >> 5], s_wv[(g >> 5) + 1], g & 31u);
+            vb &= ~(vb + 1u);
+            vb >>= c;
+            const uint32_t A = g + c;                                  // byte of the lane's window 0
+            const uint32_t QL = (uint32_t)(K2_TB - K) - A - 4u * (Q::G - 1);  // byte where its window G-1's reverse complement starts
+            uint32_t in[Q::NL], fw[Q::NS], rw[Q::NS];
 #pragma unroll
-            for (int j = 0; j < (NF + 1) / 2; j++) { const uint2 v = pf[g + j]; fw[2 * j] = v.x; fw[2 * j + 1] = v.y; }
+            for (int i = 0; i < Q::NL; i++) in[i] = fwd_w[(A >> 2) + i];
+            ackmer::preshift<Q::NS>(in, A & 3u, fw);
 #pragma unroll
-            for (int j = 0; j < (NR + 1) / 2; j++) { const uint2 v = pr[j - g]; rw[2 * j] = v.x; rw[2 * j + 1] = v.y; }
-            ackmer::process_group<K, K2_G, RC_OFF + (K2_G - 1), 0>(fw, rw, vmask >> (K2_G * g), seed, sink);
+            for (int i = 0; i < Q::NL; i++) in[i] = rc_w[(QL >> 2) + i];
+            ackmer::preshift<Q::NS>(in, QL & 3u, rw);
+            ackmer::process_quad_windows<K, 0>(fw, rw, vb, seed, sink);
         }
     }
 
@@ -195,14 +251,8 @@ __global__ void __launch_bounds__(K2_THREADS, 4) k2_hash(const uint8_t *__restri
         }
     }
     uint32_t nk = __popc(vmask);
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        nk += __shfl_xor_sync(FULL, nk, d);
-        n_rec += __shfl_xor_sync(FULL, n_rec, d);
-        n_kept += __shfl_xor_sync(FULL, n_kept, d);
-        short_len += __shfl_xor_sync(FULL, short_len, d);
-        n_bases += __shfl_xor_sync(FULL, n_bases, d);
-    }
+    nk = __reduce_add_sync(FULL, nk); n_rec = __reduce_add_sync(FULL, n_rec); n_kept = __reduce_add_sync(FULL, n_kept);
+    short_len = __reduce_add_sync(FULL, short_len); n_bases = __reduce_add_sync(FULL, n_bases);
     if ((tid & 31) == 0) {
         if (nk) atomicAdd(&s_stat[0], (unsigned long long)nk);
         if (n_rec) atomicAdd(&s_stat[1], (unsigned long long)n_rec);

@@ -277,6 +277,67 @@ AC_HD uint32_t process_run(const uint32_t *r, uint32_t win_ok, uint32_t seed, Em
     return vmask;
 }
 
+// ---- quad layout (kernel K2): a lane owns G windows at a stride of 4 bytes, so that after ONE byte
+// alignment of its words (preshift) every window's key words are whole registers: window j of the lane
+// reads forward words j .. j+NW-1 and reverse-complement words (G-1-j) .. (G-1-j)+NW-1.
+AC_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t bits /*0..31*/) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, bits);
+#else
+    return bits ? ((lo >> bits) | (hi << (32 - bits))) : lo;
+#endif
+}
+
+template <int K>
+struct QuadCfg {
+    static constexpr int G = 8;                  // windows per lane and group (4 lanes x 8 = 32 consecutive windows)
+    static constexpr int NW = (K + 3) / 4;       // words per k-mer
+    static constexpr int NS = G - 1 + NW;        // aligned words a lane needs per strand
+    static constexpr int NL = NS + 1;            // words loaded per strand (one more feeds the funnel shift)
+};
+
+// in[N+1] aligned words, off = byte offset (0..3) of the first wanted byte inside in[0] -> out[N] words starting there
+template <int N>
+AC_HD void preshift(const uint32_t *in, uint32_t off, uint32_t *out) {
+#pragma unroll
+    for (int i = 0; i < N; i++) out[i] = funnel_r(in[i], in[i + 1], 8u * off);
+}
+
+// fw / rw: the lane's pre-shifted forward / reverse-complement words (QuadCfg::NS each).
+// vbits: bit 4j set = the lane's window j may be emitted.  emit(vbits, 1 << 4j, h1) is called for every window.
+template <int K, int J, class Emit>
+AC_HD void process_quad_windows(const uint32_t *fw, const uint32_t *rw, uint32_t vbits, uint32_t seed, Emit &emit) {
+    using C = QuadCfg<K>;
+    if constexpr (J < C::G) {
+        uint32_t f[C::NW], c[C::NW];
+#pragma unroll
+        for (int m = 0; m < C::NW; m++) { f[m] = fw[J + m]; c[m] = rw[C::G - 1 - J + m]; }
+        constexpr uint32_t last_mask = (K & 3) ? ((1u << (8 * (K & 3))) - 1u) : 0xffffffffu;
+        // strand choice: the first four bases decide unless they tie (1 in 256); only the tie path needs
+        // the last words trimmed to the k-mer
+        bool use_rc;
+        if constexpr (C::NW == 1) {
+            use_rc = byte_perm(c[0] & last_mask, 0, 0x0123) < byte_perm(f[0] & last_mask, 0, 0x0123);
+        } else {
+            const uint32_t fb = byte_perm(f[0], 0, 0x0123), cb = byte_perm(c[0], 0, 0x0123);
+            if (fb != cb) use_rc = cb < fb;
+            else {
+                uint32_t ft[C::NW], ct[C::NW];
+#pragma unroll
+                for (int m = 0; m < C::NW; m++) { ft[m] = f[m]; ct[m] = c[m]; }
+                ft[C::NW - 1] &= last_mask; ct[C::NW - 1] &= last_mask;
+                use_rc = rc_is_smaller<C::NW>(ft, ct);
+            }
+        }
+        uint32_t key[C::NW];
+#pragma unroll
+        for (int m = 0; m < C::NW; m++) key[m] = use_rc ? c[m] : f[m];
+        key[C::NW - 1] &= last_mask;  // bytes past the k-mer in its last word are not part of the key
+        emit(vbits, 1u << (4 * J), murmur3_h1<K>(key, seed));
+        process_quad_windows<K, J + 1, Emit>(fw, rw, vbits, seed, emit);
+    }
+}
+
 // K1's per-byte sanitiser (scalar form; the kernel uses it per byte of a word).
 // valid ACGTacgt -> upper case, everything else -> 0x01.
 AC_HD uint32_t sanitise_byte(uint32_t c) {

@@ -29,16 +29,19 @@ def hostcheck():
     L = C.CDLL(str(so))
     L.hc_hash_stream.restype = C.c_long
     L.hc_hash_stream.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]
+    L.hc_hash_stream_quad.restype = C.c_long
+    L.hc_hash_stream_quad.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]
     L.hc_sanitise.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
     return L
 
 
-def _core_hashes(L, seq: bytes, k: int) -> np.ndarray:
+def _core_hashes(L, seq: bytes, k: int, quad: bool = False) -> np.ndarray:
     a = np.frombuffer(seq, np.uint8).copy()
     z = np.zeros_like(a)
     L.hc_sanitise(a.ctypes.data, a.size, z.ctypes.data)
     out = np.zeros(max(1, a.size), np.uint64)
-    n = L.hc_hash_stream(z.ctypes.data, z.size, k, out.ctypes.data, out.size)
+    fn = L.hc_hash_stream_quad if quad else L.hc_hash_stream
+    n = fn(z.ctypes.data, z.size, k, out.ctypes.data, out.size)
     out = out[:n]
     return out if k > 16 else out & np.uint64(0xFFFFFFFF)
 
@@ -48,6 +51,8 @@ def test_device_hash_core_matches_oracle_all_k(hostcheck, k):
     fa = oracle.read_maybe_gz(D + "NC_001416.1.fasta.gz")
     seq = b"".join(fa.split(b"\n")[1:])[:6000]
     assert np.array_equal(_core_hashes(hostcheck, seq, k), oracle.all_hashes(b">x\n" + seq + b"\n", k))
+    # the quad layout kernel K2 uses (pre-shifted words, windows at a stride of 4 bytes per lane)
+    assert np.array_equal(_core_hashes(hostcheck, seq[:3001], k, quad=True), oracle.all_hashes(b">x\n" + seq[:3001] + b"\n", k))
 
 
 def test_device_hash_core_invalid_bases(hostcheck):
@@ -56,6 +61,7 @@ def test_device_hash_core_invalid_bases(hostcheck):
                    p=[.2, .2, .2, .2, .03, .03, .03, .03, .02, .01, .01, .01, .015, .015]).astype(np.uint8).tobytes()
     for k in (27, 17, 16, 9, 32):
         assert np.array_equal(_core_hashes(hostcheck, s, k), oracle.all_hashes(b">x\n" + s + b"\n", k))
+        assert np.array_equal(_core_hashes(hostcheck, s, k, quad=True), oracle.all_hashes(b">x\n" + s + b"\n", k))
 
 
 def test_device_hash_core_full_genome_k27(hostcheck):
