@@ -59,7 +59,9 @@ struct ac_ctx {
     SelectBufs sb;
     bool sb_ok;
     uint8_t *d_Z[2];           // base stream of the segment in flight, ping-pong by segment parity
-    unsigned long long *d_st1, *d_st2;  // K1 look-back status words (state, output offset), one per tile
+    unsigned long long *d_st1, *d_st2;  // K1 (FASTA) look-back status words (state, output offset), one per tile
+    uint32_t *d_tcnt;          // K1 (FASTQ) per-tile arrays (newline count -> phase, class byte counts -> output offset)
+    size_t tile_cap;
     uint32_t seg_epoch;        // serial of the last segment launched on this context (tags the status words)
     size_t max_tiles;
     JobDev *d_jd, *h_jd;
@@ -220,10 +222,14 @@ extern "C" int ac_create(int device, ac_ctx **out) {
     if (c->seg_bytes > ((size_t)1 << 30)) c->seg_bytes = (size_t)1 << 30;
     CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) CK(cudaMalloc(&c->d_Z[i], Z_CARRY + c->seg_bytes + K2_TILE + 4096));
+    for (int i = 0; i < 2; i++) CK(cudaMalloc(&c->d_Z[i], Z_CARRY + c->seg_bytes + K1_TILE + K2_TILE + 4096));
     c->max_tiles = c->seg_bytes / K1_TILE + 4;
     CK(cudaMalloc(&c->d_st1, c->max_tiles * 8)); CK(cudaMalloc(&c->d_st2, c->max_tiles * 8));
     CK(cudaMemset(c->d_st1, 0, c->max_tiles * 8)); CK(cudaMemset(c->d_st2, 0, c->max_tiles * 8));
+    {
+        const size_t words = parse_tile_array_words(c->max_tiles, &c->tile_cap);
+        CK(cudaMalloc(&c->d_tcnt, words * 4)); CK(cudaMemset(c->d_tcnt, 0, words * 4));
+    }
     c->seg_epoch = 0;
     CK(cudaMalloc(&c->d_jd, sizeof(JobDev)));
     CK(cudaHostAlloc(&c->h_jd, sizeof(JobDev), cudaHostAllocDefault));
@@ -238,7 +244,7 @@ extern "C" void ac_destroy(ac_ctx *c) {
     if (c->active) ac_sketch_abort(c->active);  // a job cannot outlive its context
     cudaDeviceSynchronize();
     free_select(c);
-    cudaFree(c->d_Z[0]); cudaFree(c->d_Z[1]); cudaFree(c->d_st1); cudaFree(c->d_st2); cudaFree(c->d_jd); cudaFreeHost(c->h_jd);
+    cudaFree(c->d_Z[0]); cudaFree(c->d_Z[1]); cudaFree(c->d_st1); cudaFree(c->d_st2); cudaFree(c->d_tcnt); cudaFree(c->d_jd); cudaFreeHost(c->h_jd);
     for (auto &s : c->slabs) cudaFree(s.ptr);
     cudaFree(c->d_dist); cudaFree(c->d_p); cudaFree(c->d_common); cudaFree(c->d_denom); cudaFree(c->d_qmeta);
     cudaFreeHost(c->h_dist); cudaFreeHost(c->h_p); cudaFreeHost(c->h_common); cudaFreeHost(c->h_denom); cudaFreeHost(c->h_qmeta);
@@ -390,6 +396,7 @@ static int start_pass(ac_job *j, unsigned long long tau0, bool safe) {
     memset(&z, 0, sizeof(z));
     z.ps[0].at_line_start = 1;
     z.ps[0].n_zbuf = Z_CARRY;
+    z.ps[0].z_begin = Z_CARRY;
     z.tau = tau0;
     j->seg_serial = 0; j->ticket_base = 0;
     *c->h_jd = z;
@@ -438,7 +445,7 @@ static int run_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_o
     uint8_t *Z = c->d_Z[sd.serial & 1u];
     {
         ProfScope ps(c, 0);
-        launch_parse_segment(lc, sd, c->d_st1, c->d_st2, c->d_jd, c->d_Z[(sd.serial + 1u) & 1u], Z);
+        launch_parse_segment(lc, sd, c->d_st1, c->d_st2, c->d_tcnt, c->tile_cap, c->d_jd, c->d_Z[(sd.serial + 1u) & 1u], Z);
     }
     {
         ProfScope ps(c, 1);
@@ -446,7 +453,7 @@ static int run_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_o
                             c->sb.cap, j->seed, j->use64);
     }
     j->seg_serial++;
-    j->ticket_base += sd.n_tiles;
+    if (sd.fmt == FMT_FASTA) j->ticket_base += sd.n_tiles;  // only k1_fasta draws tile tickets
     CK(cudaGetLastError());
     j->first_of_stream = false;
     j->cand_bound += seg_bound;

@@ -22,7 +22,7 @@ constexpr size_t SEG_SAFE_BYTES = 32u << 20;         // segment size when every 
 constexpr int K2_THREADS = AC_K2_THREADS;             // hash CTA
 constexpr int K2_W = 32;                             // window starts per hash thread
 constexpr int K2_TILE = K2_THREADS * K2_W;           // window starts per hash CTA
-constexpr int K2_STAGE = 1024;                       // candidate staging slots per hash CTA (shared memory)
+constexpr int K2_STAGE = K2_TILE / 8;                 // candidate staging slots per hash CTA (shared memory)
 
 enum { FMT_FASTQ = 0, FMT_FASTA = 1 };
 enum {  // JobDev::format_error bits
@@ -52,7 +52,8 @@ struct ParseState {
     uint32_t fq_phase;       // FASTQ: phase (0 header,1 sequence,2 plus,3 quality) of the line holding the next byte
     uint32_t fa_type;        // FASTA: type of that line (0 header, 1 sequence)
     uint32_t at_line_start;  // the next byte begins a line
-    uint32_t n_zbuf;         // Z_CARRY + bytes the segment emitted into its Z buffer
+    uint32_t n_zbuf;         // end of the segment's base stream in its Z buffer
+    uint32_t z_begin;        // its first byte (the carry of the previous segment occupies the Z_CARRY bytes before it)
 };
 
 // Device-resident job state, updated by kernels, read back by the host at sync points.
@@ -92,7 +93,9 @@ struct LaunchCtx {
 
 // kernels' host-side launchers (defined in the .cu files)
 void launch_parse_segment(const LaunchCtx &lc, const SegDesc &sd, unsigned long long *st1, unsigned long long *st2,
-                          JobDev *jd, const uint8_t *Zprev, uint8_t *Z);
+                          uint32_t *tile_arr, size_t tile_cap, JobDev *jd, const uint8_t *Zprev, uint8_t *Z);
+// words of the FASTQ per-tile arrays for segments of up to max_tiles tiles; *tile_cap = padded entries per array
+size_t parse_tile_array_words(size_t max_tiles, size_t *tile_cap);
 // ps_slot: ParseState slot holding this segment's n_zbuf (= (serial + 1) & 1)
 void launch_hash_segment(const LaunchCtx &lc, int k, const uint8_t *Z, uint32_t max_zbuf, int ps_slot, JobDev *jd,
                          unsigned long long *cand, unsigned long long cand_cap, uint32_t seed, int use64);

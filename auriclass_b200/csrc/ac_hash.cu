@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t 
     __shared__ unsigned long long s_stat[5];  // kmers, records, kept, short_len, bases
     __shared__ __align__(8) uint64_t s_bar;
 
-    const uint32_t n_zbuf = jd->ps[ps_slot].n_zbuf;
+    const uint32_t n_zbuf = jd->ps[ps_slot].n_zbuf, z_begin = jd->ps[ps_slot].z_begin;
     const long long n_win = (long long)n_zbuf - K + 1;             // window starts 0 .. n_win-1 exist
     const long long tile_start = (long long)blockIdx.x * K2_TILE;
     // a tile is needed while it holds window starts; record-end positions p = start + K < n_zbuf
@@ -148,9 +148,9 @@ __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t 
 
     // ---- valid-window bitmap: thread t owns window starts 32t .. 32t+31 of the tile
     const long long run_start = tile_start + (long long)tid * K2_W;
-    // windows allowed by the stream range: first unprocessed start is Z_CARRY-(K-1) (earlier ones were
+    // windows allowed by the stream range: first unprocessed start is z_begin-(K-1) (earlier ones were
     // hashed with the previous segment), last is n_win-1
-    long long wlo = (long long)(Z_CARRY - (K - 1)) - run_start, whi = n_win - run_start;
+    long long wlo = (long long)z_begin - (K - 1) - run_start, whi = n_win - run_start;
     wlo = wlo < 0 ? 0 : wlo; whi = whi > K2_W ? K2_W : whi;
     uint32_t win_ok = 0;
     if (whi > wlo) win_ok = (whi >= 32 ? 0xffffffffu : ((1u << whi) - 1u)) & ~((1u << wlo) - 1u);
@@ -227,11 +227,11 @@ __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t 
     }
 
     // ---- record statistics (Mash skips records shorter than k; FASTA `length` = sum of kept lengths)
-    // positions j in [K, K+W) of the run <-> stream positions p = run_start + j in [Z_CARRY, n_zbuf)
+    // positions j in [K, K+W) of the run <-> stream positions p = run_start + j in [z_begin, n_zbuf)
     uint32_t n_rec = 0, n_kept = 0, short_len = 0, n_bases = 0;
     {
         const uint64_t sep = (uint64_t)s_sep[tid] | ((uint64_t)s_sep[tid + 1] << 32);
-        long long plo = (long long)Z_CARRY - run_start, phi = (long long)n_zbuf - run_start;
+        long long plo = (long long)z_begin - run_start, phi = (long long)n_zbuf - run_start;
         plo = plo < K ? K : plo; phi = phi > K + K2_W ? K + K2_W : phi;
         if (phi > plo) {
             const uint64_t range = ((phi >= 64) ? ~0ULL : ((1ULL << phi) - 1ULL)) & ~((1ULL << plo) - 1ULL);

@@ -5,7 +5,8 @@
 // Input: raw inflated text in HBM.  Output: the sanitised compacted base stream Z
 // (kmer_core.cuh): sequence characters only, 0x00 after/between records.
 //
-// One kernel, HBM sees the text once.  A CTA takes the next 8 KiB tile (ticket),
+// FASTA: one kernel (k1_fasta), HBM sees the text once.  FASTQ: see "count -> scan -> mask in place"
+// below (no compaction needed).  k1_fasta: a CTA takes the next 8 KiB tile (ticket),
 // every thread loads 32 bytes (two coalesced 16-byte loads) and turns them into
 // newline / line-start bit masks.  What a tile emits depends on the parser state at
 // its first byte (FASTQ: line phase 0..3, FASTA: header or sequence line) and on the
@@ -250,109 +251,141 @@ struct TileShared {
     uint32_t tile, state_in, out_off;
 };
 
-// ---------------------------------------------------------------- FASTQ
-__global__ void __launch_bounds__(K1_THREADS) k1_fastq(SegDesc sd, JobDev *__restrict__ jd, u64 *__restrict__ st1,
-                                                       u64 *__restrict__ st2, const uint8_t *__restrict__ Zprev,
-                                                       uint8_t *__restrict__ Z) {
-    __shared__ TileShared sh;
-    __shared__ __align__(16) uint32_t s_words[K1_THREADS * SW_STRIDE + 4];
-    __shared__ __align__(16) uint8_t s_out[K1_TILE + 32];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) sh.tile = (uint32_t)(atomicAdd(&jd->tile_ticket, 1u) - sd.ticket_base);
-    if (tid < 6) sh.acc[tid] = 0;
-    __syncthreads();
-    const uint32_t tile = sh.tile;
-    const ParseState ps = jd->ps[sd.serial & 1u];
-    if (tile == 0) copy_carry(sd, ps, Zprev, Z);
+// ---------------------------------------------------------------- FASTQ: count -> scan -> emit
+// What a tile emits depends on the line phase at its first byte (= newlines before it, mod 4) and on the
+// output offset (= sequence-line bytes before it).  Both are plain prefix sums over per-tile numbers, so
+// instead of chaining tiles inside one kernel (measured: with ~1200 short-lived tiles in flight the
+// look-back is the bottleneck) the FASTQ path runs three kernels per segment:
+//   k1q_count  per 8 KiB tile: newline count and the bytes in lines of local index 0..3 (mod 4)
+//   k1q_scan   one CTA: phase and output offset per tile, parser state for the next segment, carry
+//   k1q_emit   classify with the known phase, compact the sequence lines through shared memory,
+//              sanitise word-parallel, aligned 16-byte stores
+// Line classification is closed form per 32-byte chunk: two prefix-xor scans over the newline mask give
+// every byte's line index mod 4 (no per-line loop, no divergence).
 
+// exclusive prefix parity: bit i of the result = parity of popc(x & ((1 << i) - 1))
+__device__ __forceinline__ uint32_t prefix_xor_excl(uint32_t x) {
+    x <<= 1;
+    x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16;
+    return x;
+}
+
+struct LineMasks {
+    uint32_t p0, p1;  // bit i: bit 0 / bit 1 of (number of newlines in bytes [0, i) of the chunk)
+};
+__device__ __forceinline__ LineMasks line_index_masks(uint32_t nl) {
+    LineMasks lm;
+    lm.p0 = prefix_xor_excl(nl);
+    lm.p1 = prefix_xor_excl(nl & lm.p0);  // bit 1 flips at a newline that follows an odd count
+    return lm;
+}
+// bytes of the chunk that lie in lines whose index (relative to the chunk's first byte) is r (mod 4)
+__device__ __forceinline__ uint32_t lines_of(const LineMasks &lm, uint32_t r, uint32_t valid) {
+    return ((r & 1u) ? lm.p0 : ~lm.p0) & ((r & 2u) ? lm.p1 : ~lm.p1) & valid;
+}
+
+// per-tile numbers, structure of arrays (k1q_scan reads them with 16-byte loads)
+struct TileArrays {          // passed by value
+    uint32_t *nl;            // [cap] newline count            -> (k1q_scan) phase of the line holding the tile's first byte
+    uint32_t *c[4];          // [cap] bytes in lines of tile-local index r (mod 4); c[0] -> (k1q_scan) output offset
+    uint32_t *flag;          // [1]   bit 31: set by the owner of the segment's last byte, bit 0: that byte is '\n'
+};
+
+__global__ void __launch_bounds__(K1_THREADS) k1q_count(SegDesc sd, TileArrays ta) {
+    __shared__ uint32_t s_w[33];
+    __shared__ uint32_t s_acc[4];
+    const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    if (tid < 4) s_acc[tid] = 0;
     uint32_t w[8];
     ChunkMasks m;
     load_chunk(sd, tile, tid, w, m);
-#pragma unroll
-    for (int j = 0; j < 8; j++) s_words[tid * SW_STRIDE + j] = w[j];
     uint32_t total_nl;
-    const uint32_t L0 = block_excl_sum<K1_THREADS>(__popc(m.nl), sh.w, total_nl);
-    const bool prev_nl = prev_is_newline(sd, tile, m, ps.at_line_start, sh.last);
-
-    // one walk over the thread's lines: byte masks per local line index (mod 4) and what the line starts look like
-    uint32_t lm[4] = {0, 0, 0, 0};
-    uint32_t not_at = 0, not_plus = 0;  // bit r: a line with local index r (mod 4) starts here with a byte other than '@' / '+'
-    uint32_t ends = 0;
-    if (m.valid) {
-        const int vlo = __ffs(m.valid) - 1, vhi = 32 - __clz(m.valid);
-        const uint8_t *bytes = reinterpret_cast<const uint8_t *>(s_words + tid * SW_STRIDE);
-        int pos = vlo;
-        uint32_t L = L0;
-        bool ls = prev_nl;
-        while (true) {
-            const uint32_t r = L & 3u;
-            if (ls) {
-                const uint8_t ch = bytes[pos];
-                if (ch != '@') not_at |= 1u << r;
-                if (ch != '+') not_plus |= 1u << r;
-            }
-            const uint32_t rest = m.nl & (0xffffffffu << pos);
-            const int end = rest ? (__ffs(rest) - 1) : (vhi - 1);
-            const uint32_t seg = bit_range(pos, end + 1);
+    const uint32_t L0 = block_excl_sum<K1_THREADS>(__popc(m.nl), s_w, total_nl);  // syncs: s_acc is zeroed
+    const LineMasks lm = line_index_masks(m.nl);
+    // bytes per tile-local line index: chunk-local index r belongs to tile-local index (r + L0) & 3
+    uint32_t cnt[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) if (q == (int)r) lm[q] |= seg;
-            if (!rest || end + 1 >= vhi) break;
-            pos = end + 1; L++; ls = true;
-        }
-        // does this thread own the last valid byte of the tile?
+    for (int q = 0; q < 4; q++) cnt[q] = __popc(lines_of(lm, (q - L0) & 3u, m.valid));
+    uint32_t lo = cnt[0] | (cnt[1] << 16), hi = cnt[2] | (cnt[3] << 16);   // <= 32 * 32 per 16-bit field and warp
+    lo = __reduce_add_sync(FULL, lo); hi = __reduce_add_sync(FULL, hi);
+    if (lane == 0) {
+        atomicAdd(&s_acc[0], lo & 0xFFFFu); atomicAdd(&s_acc[1], lo >> 16);
+        atomicAdd(&s_acc[2], hi & 0xFFFFu); atomicAdd(&s_acc[3], hi >> 16);
+    }
+    if (m.valid) {  // the thread that owns the segment's last byte reports whether it is a newline
+        const int vhi = 32 - __clz(m.valid);
         const long long pos0 = (long long)tile * K1_TILE + (long long)tid * K1_CHUNK;
-        const long long hi = (long long)sd.skip + sd.len;
-        const long long tile_hi = min(hi, (long long)(tile + 1) * K1_TILE);
-        if (pos0 + vhi == tile_hi) ends = 0x80000000u | ((m.nl >> (vhi - 1)) & 1u);
-    }
-    if (ends) sh.acc[4] = ends;
-    {   // tile totals of the four per-line-index byte counts (two 16-bit lanes per shuffle)
-        uint32_t lo = __popc(lm[0]) | (__popc(lm[1]) << 16), hi2 = __popc(lm[2]) | (__popc(lm[3]) << 16);
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-            lo += __shfl_xor_sync(FULL, lo, d);
-            hi2 += __shfl_xor_sync(FULL, hi2, d);
-        }
-        if (lane == 0) {
-            atomicAdd(&sh.acc[0], lo & 0xFFFFu); atomicAdd(&sh.acc[1], lo >> 16);
-            atomicAdd(&sh.acc[2], hi2 & 0xFFFFu); atomicAdd(&sh.acc[3], hi2 >> 16);
-        }
+        if (pos0 + vhi == (long long)sd.skip + sd.len) *ta.flag = 0x80000000u | ((m.nl >> (vhi - 1)) & 1u);
     }
     __syncthreads();
-    if (warp == 0) {
-        // stage 1: line phase at the tile's first byte; stage 2: output offset
-        const uint32_t nl_ex = lookback<OP_SUM>(st1, tile, sd.epoch, total_nl, ps.fq_phase);
-        const uint32_t ph = nl_ex & 3u;
-        const uint32_t seq_bytes = sh.acc[(1u - ph) & 3u], qual_bytes = sh.acc[(3u - ph) & 3u];
-        const uint32_t off = lookback<OP_SUM>(st2, tile, sd.epoch, seq_bytes, Z_CARRY);
-        if (lane == 0) {
-            sh.state_in = ph; sh.out_off = off;
-            if (seq_bytes) atomicAdd(&jd->fq_seq_bytes, (u64)seq_bytes);
-            if (qual_bytes) atomicAdd(&jd->fq_qual_bytes, (u64)qual_bytes);
-        }
-    }
-    __syncthreads();
-    const uint32_t ph = sh.state_in, out_off = sh.out_off;
-    const uint32_t r_seq = (1u - ph) & 3u, r_hdr = (0u - ph) & 3u, r_plus = (2u - ph) & 3u;
-    uint32_t emit = 0;
-#pragma unroll
-    for (int q = 0; q < 4; q++) if (q == (int)r_seq) emit = lm[q];
-    uint32_t err = 0;
-    if ((not_at >> r_hdr) & 1u) err |= FERR_FQ_HEADER;
-    if ((not_plus >> r_plus) & 1u) err |= FERR_FQ_PLUS;
-    if (err) atomicOr(&jd->format_error, err);
-    uint32_t total_emit;
-    const uint32_t E = block_excl_sum<K1_THREADS>(__popc(emit), sh.w, total_emit);  // also orders s_words
-    const uint32_t s_off = out_off & 15u;
-    compact_runs(s_words, s_out, tid, emit, s_off + E);
-    __syncthreads();
-    write_out(s_out, s_off, total_emit, Z, out_off);
+    if (tid == 0) ta.nl[tile] = total_nl;
+    if (tid == 0) { ta.c[0][tile] = s_acc[0]; ta.c[1][tile] = s_acc[1]; ta.c[2][tile] = s_acc[2]; ta.c[3][tile] = s_acc[3]; }
+}
 
-    if (tile + 1 == sd.n_tiles && tid == 0) {  // last tile: parser state for the next segment / file
-        const uint32_t end_state = (ph + total_nl) & 3u;
-        const uint32_t ends_nl = (sh.acc[4] & 0x80000000u) ? (sh.acc[4] & 1u) : ps.at_line_start;
+constexpr int SCAN_T = 1024;
+constexpr int SCAN_PER = 8;                        // tiles per thread and round: two 16-byte loads per array
+constexpr int SCAN_ROUND = SCAN_T * SCAN_PER;      // 8192 tiles = 64 MiB of text per round
+
+__global__ void __launch_bounds__(SCAN_T) k1q_scan(SegDesc sd, TileArrays ta, JobDev *__restrict__ jd,
+                                                   const uint8_t *__restrict__ Zprev, uint8_t *__restrict__ Z) {
+    __shared__ uint32_t s_w[33];
+    const uint32_t tid = threadIdx.x, n = sd.n_tiles;
+    const ParseState ps = jd->ps[sd.serial & 1u];
+    copy_carry(sd, ps, Zprev, Z);
+    uint32_t phase_run = ps.fq_phase, off_run = Z_CARRY;
+    unsigned long long qual_total = 0;
+    for (uint32_t r0 = 0; r0 < n; r0 += SCAN_ROUND) {   // the arrays are padded to a multiple of SCAN_ROUND
+        const uint32_t t0 = r0 + tid * SCAN_PER;
+        uint32_t nl[SCAN_PER], c[4][SCAN_PER];
+#pragma unroll
+        for (int v = 0; v < SCAN_PER / 4; v++) {
+            const uint4 x = reinterpret_cast<const uint4 *>(ta.nl + t0)[v];
+            nl[4 * v] = x.x; nl[4 * v + 1] = x.y; nl[4 * v + 2] = x.z; nl[4 * v + 3] = x.w;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint4 y = reinterpret_cast<const uint4 *>(ta.c[q] + t0)[v];
+                c[q][4 * v] = y.x; c[q][4 * v + 1] = y.y; c[q][4 * v + 2] = y.z; c[q][4 * v + 3] = y.w;
+            }
+        }
+        uint32_t local_nl = 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_PER; i++) { if (t0 + i >= n) nl[i] = 0; local_nl += nl[i]; }
+        uint32_t tot_nl;
+        uint32_t run = block_excl_sum<SCAN_T>(local_nl, s_w, tot_nl) + phase_run;
+        uint32_t ph[SCAN_PER], outb[SCAN_PER], local_out = 0, local_q = 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_PER; i++) {
+            ph[i] = run & 3u;
+            run += nl[i];
+            const uint32_t rs = (1u - ph[i]) & 3u, rq = (3u - ph[i]) & 3u;
+            uint32_t sb = 0, qb = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) { if (q == (int)rs) sb = c[q][i]; if (q == (int)rq) qb = c[q][i]; }
+            if (t0 + i >= n) { sb = 0; qb = 0; }
+            outb[i] = sb; local_out += sb; local_q += qb;
+        }
+        uint32_t tot_out, tot_q;
+        uint32_t off = block_excl_sum<SCAN_T>(local_out, s_w, tot_out) + off_run;
+        block_excl_sum<SCAN_T>(local_q, s_w, tot_q);
+#pragma unroll
+        for (int i = 0; i < SCAN_PER; i++) { const uint32_t o = off; off += outb[i]; outb[i] = o; }
+#pragma unroll
+        for (int v = 0; v < SCAN_PER / 4; v++) {
+            reinterpret_cast<uint4 *>(ta.nl + t0)[v] = make_uint4(ph[4 * v], ph[4 * v + 1], ph[4 * v + 2], ph[4 * v + 3]);
+            reinterpret_cast<uint4 *>(ta.c[0] + t0)[v] = make_uint4(outb[4 * v], outb[4 * v + 1], outb[4 * v + 2], outb[4 * v + 3]);
+        }
+        phase_run += tot_nl; off_run += tot_out; qual_total += tot_q;
+    }
+    if (tid == 0) {
+        const uint32_t ends = *ta.flag;
+        *ta.flag = 0;
+        const uint32_t end_state = phase_run & 3u;
+        const uint32_t ends_nl = (ends & 0x80000000u) ? (ends & 1u) : ps.at_line_start;
+        jd->fq_seq_bytes += off_run - Z_CARRY;   // single writer: no other kernel of the job touches these
+        jd->fq_qual_bytes += qual_total;
         ParseState nx;
-        nx.n_zbuf = out_off + total_emit;
+        nx.z_begin = Z_CARRY;
+        nx.n_zbuf = off_run;
         if (sd.last_of_file) {
             if (end_state != 0 || !ends_nl) atomicOr(&jd->format_error, (uint32_t)FERR_FQ_TRUNC);
             nx.fq_phase = 0; nx.fa_type = 0; nx.at_line_start = 1;
@@ -361,6 +394,47 @@ __global__ void __launch_bounds__(K1_THREADS) k1_fastq(SegDesc sd, JobDev *__res
         }
         jd->ps[(sd.serial + 1u) & 1u] = nx;
     }
+}
+
+__global__ void __launch_bounds__(K1_THREADS) k1q_emit(SegDesc sd, TileArrays ta, JobDev *__restrict__ jd, uint8_t *__restrict__ Z) {
+    __shared__ uint32_t s_w[33];
+    __shared__ uint32_t s_last[8];
+    __shared__ __align__(16) uint32_t s_words[K1_THREADS * SW_STRIDE + 4];
+    __shared__ __align__(16) uint8_t s_out[K1_TILE + 32];
+    const uint32_t tile = blockIdx.x, tid = threadIdx.x;
+    const uint32_t tile_phase = ta.nl[tile], out_off = ta.c[0][tile];
+    const ParseState ps = jd->ps[sd.serial & 1u];
+    uint32_t w[8];
+    ChunkMasks m;
+    load_chunk(sd, tile, tid, w, m);
+#pragma unroll
+    for (int j = 0; j < 8; j++) s_words[tid * SW_STRIDE + j] = w[j];
+    uint32_t total_nl;
+    const uint32_t L0 = block_excl_sum<K1_THREADS>(__popc(m.nl), s_w, total_nl);
+    const bool prev_nl = prev_is_newline(sd, tile, m, ps.at_line_start, s_last);
+    const LineMasks lm = line_index_masks(m.nl);
+    const uint32_t ph = (tile_phase + L0) & 3u;       // phase of the line holding the chunk's first byte
+    const uint32_t emit = lines_of(lm, (1u - ph) & 3u, m.valid);   // sequence lines, newline included (-> separator)
+    // format checks on the line starts of this chunk: headers start with '@', third lines with '+'
+    uint32_t err = 0;
+    const uint32_t ls = m.valid ? (((m.nl << 1) | (prev_nl ? (m.valid & (0u - m.valid)) : 0u)) & m.valid) : 0u;
+    if (ls) {
+        const uint32_t hdr = lines_of(lm, (0u - ph) & 3u, m.valid), plus = lines_of(lm, (2u - ph) & 3u, m.valid);
+        const uint8_t *bytes = reinterpret_cast<const uint8_t *>(s_words + tid * SW_STRIDE);
+        for (uint32_t x = ls & (hdr | plus); x; x &= x - 1) {
+            const int pos = __ffs(x) - 1;
+            const uint8_t ch = bytes[pos];
+            if ((hdr >> pos) & 1u) { if (ch != '@') err |= FERR_FQ_HEADER; }
+            else if (ch != '+') err |= FERR_FQ_PLUS;
+        }
+    }
+    if (err) atomicOr(&jd->format_error, err);
+    uint32_t total_emit;
+    const uint32_t E = block_excl_sum<K1_THREADS>(__popc(emit), s_w, total_emit);  // also orders s_words
+    const uint32_t s_off = out_off & 15u;
+    compact_runs(s_words, s_out, tid, emit, s_off + E);
+    __syncthreads();
+    write_out(s_out, s_off, total_emit, Z, out_off);
 }
 
 // ---------------------------------------------------------------- FASTA
@@ -488,6 +562,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_fasta(SegDesc sd, JobDev *__res
             nx.fq_phase = ps.fq_phase; nx.fa_type = end_state; nx.at_line_start = ends_nl;
         }
         nx.n_zbuf = nz;
+        nx.z_begin = Z_CARRY;
         jd->ps[(sd.serial + 1u) & 1u] = nx;
     }
 }
@@ -495,11 +570,26 @@ __global__ void __launch_bounds__(K1_THREADS) k1_fasta(SegDesc sd, JobDev *__res
 }  // namespace
 
 void launch_parse_segment(const LaunchCtx &lc, const SegDesc &sd, unsigned long long *st1, unsigned long long *st2,
-                          JobDev *jd, const uint8_t *Zprev, uint8_t *Z) {
+                          uint32_t *tile_arr, size_t tile_cap, JobDev *jd, const uint8_t *Zprev, uint8_t *Z) {
     // sd.n_tiles >= 1 (an empty segment still threads the parser state through its single tile)
-    if (sd.fmt == FMT_FASTQ) k1_fastq<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, jd, st1, st2, Zprev, Z);
-    else k1_fasta<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, jd, st1, st2, Zprev, Z);
-    ++*lc.launches;
+    if (sd.fmt == FMT_FASTQ) {
+        TileArrays ta;
+        ta.nl = tile_arr;
+        for (int q = 0; q < 4; q++) ta.c[q] = tile_arr + (size_t)(q + 1) * tile_cap;
+        ta.flag = tile_arr + 5 * tile_cap;
+        k1q_count<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, ta);
+        k1q_scan<<<1, SCAN_T, 0, lc.stream>>>(sd, ta, jd, Zprev, Z);
+        k1q_emit<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, ta, jd, Z);
+        *lc.launches += 3;
+    } else {
+        k1_fasta<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, jd, st1, st2, Zprev, Z);
+        ++*lc.launches;
+    }
+}
+size_t parse_tile_array_words(size_t max_tiles, size_t *tile_cap) {
+    const size_t cap = ((max_tiles + SCAN_ROUND - 1) / SCAN_ROUND) * SCAN_ROUND;  // k1q_scan reads whole rounds
+    *tile_cap = cap;
+    return 5 * cap + 4;
 }
 
 }  // namespace ac
