@@ -10,6 +10,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
+#include <set>
 #include <vector>
 
 #include "../../include/auriclass_cuda.h"
@@ -34,6 +36,20 @@ static int fail(int code, const char *fmt, ...) {
                         cudaGetErrorString(e_), __FILE__, __LINE__);                                      \
     } while (0)
 
+// AC_TRACE=1: host wall-clock of the phases of ac_sketch_end on stderr (tuning aid)
+#include <chrono>
+static bool trace_on() { static int v = -1; if (v < 0) { const char *e = getenv("AC_TRACE"); v = (e && *e && *e != '0') ? 1 : 0; } return v == 1; }
+struct Trace {
+    std::chrono::steady_clock::time_point t0;
+    Trace() : t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) {
+        if (!trace_on()) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ac trace] %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 // ------------------------------------------------------------------ types
 struct Slab {
     uint8_t *ptr;
@@ -48,6 +64,10 @@ struct Piece {                 // contiguous raw text of one file, in stream ord
     cudaEvent_t ready;         // H2D copy of the piece's latest bytes (nullptr for device feeds)
 };
 
+// Sketch buffers are recycled through their creating context: cudaMalloc / cudaFree of the last sub-allocation of a
+// driver block maps / unmaps the block and synchronises the device (milliseconds per isolate otherwise).
+struct SketchBuf { unsigned long long *h; uint32_t *c; uint64_t cap; };
+
 struct ac_ctx {
     int dev;
     cudaStream_t s_copy, s_comp;
@@ -58,6 +78,8 @@ struct ac_ctx {
     size_t seg_bytes;          // raw text per segment (SEG_BYTES, or AC_SEG_MB for tests)
     SelectBufs sb;
     bool sb_ok;
+    CountTable ct;             // count table of speculative passes (key/cnt/qhist owned here; qlist aliases sb.keys_b)
+    int ct_log2;               // log2(slots), AC_TABLE_LOG2
     uint8_t *d_Z[2];           // base stream of the segment in flight, ping-pong by segment parity
     unsigned long long *d_st1, *d_st2;  // K1 (FASTA) look-back status words (state, output offset), one per tile
     uint32_t *d_tcnt;          // K1 (FASTQ) per-tile arrays (newline count -> phase, class byte counts -> output offset)
@@ -75,6 +97,7 @@ struct ac_ctx {
     unsigned long long *d_qmeta, *h_qmeta;  // [3][max_q]: pointer, n, length
     size_t dist_cap, q_cap;
     std::vector<cudaEvent_t> ev_pool;
+    std::vector<SketchBuf> sk_pool;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[3];
     cudaEvent_t ev_job0, ev_job1;
 };
@@ -94,6 +117,7 @@ struct ac_job {
     bool pass_started;
     unsigned long long tau0;
     bool safe;
+    bool table;                       // the pass counts its candidates in the count table (speculative passes), not by sorting
     int passes;
     size_t proc_piece, proc_off;      // first unprocessed byte
     size_t pending;                   // fed but unprocessed bytes
@@ -112,9 +136,14 @@ struct ac_sketch {
     unsigned long long *d_hash;
     uint32_t *d_cnt;
     uint64_t n;
+    uint64_t cap;              // entries allocated (>= n): decides whether a pooled buffer pair can be reused
     int k, s, hash_bits;
     uint64_t length;
 };
+
+// A sketch may outlive its context, so before its buffers go back to the context's pool liveness is checked here.
+static std::mutex g_ctx_mu;
+static std::set<ac_ctx *> g_live_ctx;
 
 struct ac_refs {
     ac_ctx *ctx;
@@ -167,7 +196,33 @@ static void free_select(ac_ctx *c) {
     cudaFree(b.tab_hash); cudaFree(b.tab_cnt); cudaFree(b.start_sum); cudaFree(b.hist); cudaFree(b.tile_tmp);
     cudaFree(b.sk_hash); cudaFree(b.sk_cnt);
     memset(&b, 0, sizeof(b));
+    cudaFree(c->ct.key); cudaFree(c->ct.cnt); cudaFree(c->ct.qhist);
+    memset(&c->ct, 0, sizeof(c->ct));
     c->sb_ok = false;
+}
+
+// device buffers for a sketch of n entries: a pooled pair when one is big enough, else fresh allocations
+static cudaError_t sketch_buf_get(ac_ctx *c, uint64_t n, SketchBuf *out) {
+    const uint64_t want = n ? n : 1;
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        for (size_t i = 0; i < c->sk_pool.size(); i++)
+            if (c->sk_pool[i].cap >= want) { *out = c->sk_pool[i]; c->sk_pool.erase(c->sk_pool.begin() + i); return cudaSuccess; }
+    }
+    out->h = nullptr; out->c = nullptr; out->cap = want;
+    cudaError_t e = cudaMalloc(&out->h, want * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&out->c, want * 4);
+    if (e != cudaSuccess) { cudaFree(out->h); cudaFree(out->c); out->h = nullptr; out->c = nullptr; }
+    return e;
+}
+static void sketch_buf_put(ac_ctx *c, int dev, const SketchBuf &b) {
+    if (!b.h && !b.c) return;
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        if (c && g_live_ctx.count(c) && c->sk_pool.size() < 64) { c->sk_pool.push_back(b); return; }
+    }
+    cudaSetDevice(dev);
+    cudaFree(b.h); cudaFree(b.c);
 }
 
 static int alloc_select(ac_ctx *c, size_t sk_cap) {
@@ -191,6 +246,15 @@ static int alloc_select(ac_ctx *c, size_t sk_cap) {
     CK(cudaMalloc(&b.tile_tmp, (2 * (cap / 2048 + 2)) * 4));
     CK(cudaMalloc(&b.sk_hash, sk_cap * 8)); CK(cudaMalloc(&b.sk_cnt, sk_cap * 4));
     c->sk_cap = sk_cap;
+    {
+        const size_t slots = (size_t)1 << c->ct_log2;
+        memset(&c->ct, 0, sizeof(c->ct));
+        CK(cudaMalloc(&c->ct.key, slots * 8)); CK(cudaMalloc(&c->ct.cnt, slots * 4));
+        CK(cudaMalloc(&c->ct.qhist, ((size_t)1 << CT_BUCKET_BITS) * 4));
+        c->ct.mask = (uint32_t)(slots - 1);
+        c->ct.qlist = b.keys_b;   // the sort scratch is idle while a table pass runs
+        c->ct.qcap = (uint32_t)std::min<size_t>(cap, 0xffffffffu);
+    }
     c->sb_ok = true;
     return AC_OK;
 }
@@ -216,6 +280,11 @@ extern "C" int ac_create(int device, ac_ctx **out) {
     const char *cap_env = getenv("AC_CAND_CAP");
     c->cand_cap = cap_env ? (size_t)strtoull(cap_env, nullptr, 10) : ((size_t)48 << 20);
     if (c->cand_cap < (1u << 16)) c->cand_cap = 1u << 16;
+    const char *tab_env = getenv("AC_TABLE_LOG2");
+    c->ct_log2 = tab_env ? atoi(tab_env) : 23;   // 8 Mi slots (96 MB): C. auris at 200x leaves it under 40 % full
+    if (c->ct_log2 < 10) c->ct_log2 = 10;
+    if (c->ct_log2 > 30) c->ct_log2 = 30;
+    memset(&c->ct, 0, sizeof(c->ct));
     const char *seg_env = getenv("AC_SEG_MB");
     c->seg_bytes = seg_env ? ((size_t)strtoull(seg_env, nullptr, 10) << 20) : SEG_BYTES;
     if (c->seg_bytes < ((size_t)1 << 20)) c->seg_bytes = (size_t)1 << 20;
@@ -234,6 +303,7 @@ extern "C" int ac_create(int device, ac_ctx **out) {
     CK(cudaMalloc(&c->d_jd, sizeof(JobDev)));
     CK(cudaHostAlloc(&c->h_jd, sizeof(JobDev), cudaHostAllocDefault));
     CK(cudaEventCreate(&c->ev_job0)); CK(cudaEventCreate(&c->ev_job1));
+    { std::lock_guard<std::mutex> lk(g_ctx_mu); g_live_ctx.insert(c); }
     *out = c;
     return AC_OK;
 }
@@ -242,7 +312,10 @@ extern "C" void ac_destroy(ac_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->dev);
     if (c->active) ac_sketch_abort(c->active);  // a job cannot outlive its context
+    { std::lock_guard<std::mutex> lk(g_ctx_mu); g_live_ctx.erase(c); }
     cudaDeviceSynchronize();
+    for (auto &b : c->sk_pool) { cudaFree(b.h); cudaFree(b.c); }
+    c->sk_pool.clear();
     free_select(c);
     cudaFree(c->d_Z[0]); cudaFree(c->d_Z[1]); cudaFree(c->d_st1); cudaFree(c->d_st2); cudaFree(c->d_tcnt); cudaFree(c->d_jd); cudaFreeHost(c->h_jd);
     for (auto &s : c->slabs) cudaFree(s.ptr);
@@ -332,7 +405,7 @@ extern "C" int ac_sketch_begin(ac_ctx *c, int k, int sketch_size, uint32_t seed,
     j->ctx = c; j->k = k; j->s = sketch_size; j->m = (mode == AC_MODE_FASTA) ? 1 : min_copies; j->mode = mode;
     j->use64 = k > 16 ? 1 : 0; j->seed = seed;
     j->cur_file = -1; j->file_open = false; j->cur_fmt = -1; j->tail_len = 0;
-    j->pass_started = false; j->tau0 = 0; j->safe = false; j->passes = 0;
+    j->pass_started = false; j->tau0 = 0; j->safe = false; j->table = false; j->passes = 0;
     j->proc_piece = 0; j->proc_off = 0; j->pending = 0; j->first_of_stream = true;
     j->cand_bound = 0; j->n_table_host = 0; j->tau_host = 0; j->bytes_done = 0; j->next_mark = 0; j->ended_local = false;
     for (auto &s : c->slabs) s.used = 0;
@@ -402,10 +475,19 @@ static int start_pass(ac_job *j, unsigned long long tau0, bool safe) {
     *c->h_jd = z;
     CK(cudaMemcpyAsync(c->d_jd, c->h_jd, sizeof(JobDev), cudaMemcpyHostToDevice, c->s_comp));
     CK(cudaStreamSynchronize(c->s_comp));
+    if (j->passes == 0) CK(cudaEventRecord(c->ev_job0, c->s_comp));   // device time of a job starts before its table is cleared
+    j->table = !safe && tau0 != space_max(j);
+    if (j->table) {
+        const size_t slots = (size_t)c->ct.mask + 1;
+        CK(cudaMemsetAsync(c->ct.key, 0xff, slots * 8, c->s_comp));
+        CK(cudaMemsetAsync(c->ct.cnt, 0, slots * 4, c->s_comp));
+        CK(cudaMemsetAsync(c->ct.qhist, 0, ((size_t)1 << CT_BUCKET_BITS) * 4, c->s_comp));
+        c->ct.min_copies = (uint32_t)j->m;
+        c->ct.bshift = std::max(0, key_bits_for(tau0) - CT_BUCKET_BITS);
+    }
     j->pass_started = true; j->tau0 = tau0; j->safe = safe; j->passes++;
     j->proc_piece = 0; j->proc_off = 0; j->first_of_stream = true;
     j->cand_bound = 0; j->n_table_host = 0; j->tau_host = tau0; j->bytes_done = 0; j->next_mark = c->seg_bytes;
-    if (j->passes == 1) CK(cudaEventRecord(c->ev_job0, c->s_comp));
     return AC_OK;
 }
 
@@ -419,7 +501,7 @@ static int run_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_o
     // candidate-buffer headroom: consolidate first when this segment could overflow it
     const double frac = j->safe ? 1.0 : std::min(1.0, ((double)j->tau_host + 1.0) / ((double)space_max(j) + 1.0) * 2.0 + 1e-3);
     const double seg_bound = j->safe ? (double)seg_len : (double)seg_len * frac + 65536.0;
-    if (j->cand_bound > 0 && j->cand_bound + seg_bound + j->n_table_host > (double)c->sb.cap) {
+    if (!j->table && j->cand_bound > 0 && j->cand_bound + seg_bound + j->n_table_host > (double)c->sb.cap) {
         int rc = consolidate(j);
         if (rc) return rc;
     }
@@ -449,8 +531,10 @@ static int run_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_o
     }
     {
         ProfScope ps(c, 1);
+        CountTable off;
+        memset(&off, 0, sizeof(off));
         launch_hash_segment(lc, j->k, Z, (uint32_t)(Z_CARRY + seg_len + 1), (int)((sd.serial + 1u) & 1u), c->d_jd, c->sb.keys_a,
-                            c->sb.cap, j->seed, j->use64);
+                            c->sb.cap, j->seed, j->use64, j->table ? c->ct : off);
     }
     j->seg_serial++;
     if (sd.fmt == FMT_FASTA) j->ticket_base += sd.n_tiles;  // only k1_fasta draws tile tickets
@@ -458,6 +542,16 @@ static int run_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_o
     j->first_of_stream = false;
     j->cand_bound += seg_bound;
     j->bytes_done += seg_len;
+    if (j->table) {
+        // the threshold follows the histogram of qualified keys: a 5 us kernel, no host round trip.  Early
+        // segments pull tau from the speculative 1/16 down to ~1.3x its final value; later ones barely move it.
+        if (j->seg_serial <= 4 || (j->seg_serial & 3u) == 0) {
+            ProfScope ps(c, 2);
+            launch_table_tau_update(lc, c->ct, c->d_jd, j->s);
+            CK(cudaGetLastError());
+        }
+        return AC_OK;
+    }
     if (j->safe || j->bytes_done >= j->next_mark) {
         int rc = consolidate(j);
         if (rc) return rc;
@@ -486,7 +580,9 @@ static int pump(ac_job *j, bool all) {
         if (!j->pass_started) {
             // the size fed so far decides the speculative threshold: big inputs start at 1/16 of
             // the hash space, small ones keep everything (tau = max, nothing to verify)
-            const bool big = j->pending >= std::min(SEG_SAFE_BYTES, j->ctx->seg_bytes);
+            // (tau0 = 1/16 must leave >= s qualified hashes: ~128 bytes of text per sketch entry at the least)
+            const size_t spec_min = std::max((size_t)4 << 20, (size_t)128 * (size_t)j->s);
+            const bool big = j->pending >= std::min(spec_min, j->ctx->seg_bytes);
             int rc = start_pass(j, big ? (space_max(j) >> 4) : space_max(j), !big);
             if (rc) return rc;
         }
@@ -666,21 +762,55 @@ static void fill_info(const ac_job *j, const JobDev &h, ac_sketch_info *info) {
     info->passes = j->passes;
 }
 
+// end of a count-table pass: final threshold, then the qualified keys <= tau (for_exchange: every key <= tau)
+// are collected, sorted and laid out as table + sketch prefix exactly as a consolidation leaves them
+static int finish_table(ac_job *j, bool for_exchange) {
+    ac_ctx *c = j->ctx;
+    LaunchCtx lc{c->s_comp, &c->launches};
+    ProfScope ps(c, 2);
+    launch_table_tau_update(lc, c->ct, c->d_jd, j->s);
+    CK(cudaGetLastError());
+    int rc = read_jd(c);
+    if (rc) return rc;
+    const JobDev &h = *c->h_jd;
+    if (h.overflow) return AC_OK;                                   // table or list full: the caller repeats the pass by sorting
+    if (h.n_qualified < (uint32_t)j->s) return AC_OK;               // speculation failed: the caller repeats it with tau = max
+    const uint32_t n_q = h.n_qualified;
+    const int bits = key_bits_for(h.tau);
+    uint32_t n = n_q;
+    if (for_exchange) {
+        launch_table_export(lc, c->ct, c->sb, c->d_jd);
+        CK(cudaGetLastError());
+        rc = read_jd(c);
+        if (rc) return rc;
+        n = c->h_jd->n_out;
+        if (n > c->sb.cap) return fail(AC_E_NOMEM, "exchange table needs %u entries, capacity %zu (raise AC_CAND_CAP)", n, c->sb.cap);
+    } else {
+        launch_table_collect(lc, c->ct, c->sb, c->d_jd, h.n_qlist);
+    }
+    launch_table_finish(lc, c->sb, c->d_jd, n, n_q, bits, j->s, for_exchange ? 1 : 0);
+    CK(cudaGetLastError());
+    return AC_OK;
+}
+
 // finish the local pass (all ranks): returns with the final table on the device and h_jd current
-static int finish_local(ac_job *j) {
+static int finish_local(ac_job *j, bool for_exchange = false) {
     ac_ctx *c = j->ctx;
     if (j->file_open) close_file(j);
+    Trace tr;
     for (int attempt = 0; attempt < 4; attempt++) {
         int rc = pump(j, true);
         if (rc) return rc;
+        tr.mark("  pump(all)");
         if (!j->pass_started) {  // nothing was fed at all
             rc = start_pass(j, space_max(j), true);
             if (rc) return rc;
         }
-        rc = consolidate(j);
+        rc = j->table ? finish_table(j, for_exchange) : consolidate(j);
         if (rc) return rc;
         rc = read_jd(c);
         if (rc) return rc;
+        tr.mark("  table/consolidate");
         const JobDev &h = *c->h_jd;
         uint32_t ferr = h.format_error;
         if (h.fq_seq_bytes != h.fq_qual_bytes) ferr |= FERR_FQ_TRUNC;  // sequence and quality byte totals of the job differ
@@ -708,9 +838,9 @@ static int make_sketch(ac_ctx *c, const unsigned long long *d_hash, const uint32
                        int hash_bits, uint64_t length, ac_sketch **out) {
     ac_sketch *sk = new ac_sketch();
     sk->ctx = c; sk->dev = c->dev; sk->n = n; sk->k = k; sk->s = s; sk->hash_bits = hash_bits; sk->length = length;
-    sk->d_hash = nullptr; sk->d_cnt = nullptr;
-    cudaError_t e = cudaMalloc(&sk->d_hash, (n ? n : 1) * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&sk->d_cnt, (n ? n : 1) * 4);
+    SketchBuf b;
+    cudaError_t e = sketch_buf_get(c, n, &b);
+    sk->d_hash = b.h; sk->d_cnt = b.c; sk->cap = b.cap;
     if (e == cudaSuccess && n) e = cudaMemcpyAsync(sk->d_hash, d_hash, n * 8, cudaMemcpyDeviceToDevice, c->s_comp);
     if (e == cudaSuccess && n) {
         if (d_cnt) e = cudaMemcpyAsync(sk->d_cnt, d_cnt, n * 4, cudaMemcpyDeviceToDevice, c->s_comp);
@@ -718,7 +848,7 @@ static int make_sketch(ac_ctx *c, const unsigned long long *d_hash, const uint32
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_comp);
     if (e != cudaSuccess) {
-        cudaFree(sk->d_hash); cudaFree(sk->d_cnt); delete sk;
+        sketch_buf_put(c, c->dev, b); delete sk;
         return fail(AC_E_CUDA, "sketch allocation/copy failed: %s", cudaGetErrorString(e));
     }
     *out = sk;
@@ -730,8 +860,10 @@ extern "C" int ac_sketch_end(ac_job *j, ac_sketch **out, ac_sketch_info *info) {
     *out = nullptr;
     ac_ctx *c = j->ctx;
     cudaSetDevice(c->dev);
+    Trace tr;
     int rc = finish_local(j);
     if (rc) { job_free(j); return rc; }
+    tr.mark("finish_local");
     LaunchCtx lc{c->s_comp, &c->launches};
     {
         ProfScope ps(c, 2);
@@ -740,6 +872,7 @@ extern "C" int ac_sketch_end(ac_job *j, ac_sketch **out, ac_sketch_info *info) {
     cudaEventRecord(c->ev_job1, c->s_comp);
     rc = read_jd(c);
     if (rc) { job_free(j); return rc; }
+    tr.mark("finalize+read");
     prof_collect(c);
     const JobDev h = *c->h_jd;
     fill_info(j, h, info);
@@ -751,7 +884,9 @@ extern "C" int ac_sketch_end(ac_job *j, ac_sketch **out, ac_sketch_info *info) {
     }
     const uint64_t length = (j->mode == AC_MODE_FASTA) ? (h.n_bases - h.n_short_len) : (uint64_t)h.genome_size;
     rc = make_sketch(c, c->sb.sk_hash, c->sb.sk_cnt, h.n_sketch, j->k, j->s, j->use64 ? 64 : 32, length, out);
+    tr.mark("make_sketch");
     job_free(j);
+    tr.mark("job_free");
     return rc;
 }
 
@@ -760,7 +895,7 @@ extern "C" int ac_sketch_end_local(ac_job *j, uint64_t *n_entries, uint64_t *tau
     if (!j) return fail(AC_E_PARAM, "job is NULL");
     ac_ctx *c = j->ctx;
     CK(cudaSetDevice(c->dev));
-    int rc = finish_local(j);
+    int rc = finish_local(j, true);
     if (rc) return rc;
     const JobDev &h = *c->h_jd;
     j->ended_local = true;
@@ -874,12 +1009,12 @@ extern "C" int ac_sketch_from_hashes(ac_ctx *c, const uint64_t *hashes, uint64_t
     CK(cudaSetDevice(c->dev));
     ac_sketch *sk = new ac_sketch();
     sk->ctx = c; sk->dev = c->dev; sk->n = n; sk->k = k; sk->s = sketch_size; sk->hash_bits = k > 16 ? 64 : 32; sk->length = length;
-    sk->d_hash = nullptr; sk->d_cnt = nullptr;
-    cudaError_t e = cudaMalloc(&sk->d_hash, (n ? n : 1) * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&sk->d_cnt, (n ? n : 1) * 4);
+    SketchBuf b;
+    cudaError_t e = sketch_buf_get(c, n, &b);
+    sk->d_hash = b.h; sk->d_cnt = b.c; sk->cap = b.cap;
     if (e == cudaSuccess && n) e = cudaMemcpy(sk->d_hash, hashes, n * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && n) e = cudaMemset(sk->d_cnt, 0, n * 4);
-    if (e != cudaSuccess) { cudaFree(sk->d_hash); cudaFree(sk->d_cnt); delete sk; return fail(AC_E_CUDA, "sketch upload failed: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { sketch_buf_put(c, c->dev, b); delete sk; return fail(AC_E_CUDA, "sketch upload failed: %s", cudaGetErrorString(e)); }
     *out = sk;
     return AC_OK;
 }
@@ -894,8 +1029,7 @@ extern "C" int ac_sketch_hashes(const ac_sketch *sk, uint64_t *hashes, uint32_t 
 }
 extern "C" void ac_sketch_free(ac_sketch *sk) {
     if (!sk) return;
-    cudaSetDevice(sk->dev);
-    cudaFree(sk->d_hash); cudaFree(sk->d_cnt);
+    sketch_buf_put(sk->ctx, sk->dev, SketchBuf{sk->d_hash, sk->d_cnt, sk->cap});
     delete sk;
 }
 

@@ -74,12 +74,31 @@ struct JobDev {
     uint32_t n_qualified;           // entries of the table with count >= m (capped view: see select)
     uint32_t n_sketch;              // min(s, n_qualified)
     unsigned long long total_vals;  // scratch
+    uint32_t n_qlist;               // count-table mode: keys whose count reached min_copies so far (entries of the qualified list)
+    uint32_t n_out;                 // count-table mode: entries written by the collect / export kernels
     // result (K4)
     unsigned long long max_hash, sum_counts;
     double genome_size, coverage;
 };
 
-struct JobCounters;  // (reserved)
+// Count table of the speculative pass (tau0 < max): an open-addressing hash table keyed by the hash itself
+// (hashes <= tau only, so the all-ones key is free to mean "empty"), exact occurrence counts, the list of keys
+// whose count reached min_copies, and a 65,536-bucket histogram of those keys by their top bits below tau0.
+// K2 inserts its candidates straight into it; the threshold follows from the histogram (k3t_tau_update) and
+// the sketch from the qualified list -- the candidate stream is never sorted.
+constexpr unsigned long long CT_EMPTY = ~0ULL;
+constexpr int CT_BUCKET_BITS = 16;
+constexpr int CT_MAX_PROBE = 512;
+struct CountTable {              // passed by value to the kernels
+    unsigned long long *key;     // [mask + 1]
+    uint32_t *cnt;               // [mask + 1]
+    uint32_t *qhist;             // [1 << CT_BUCKET_BITS]
+    unsigned long long *qlist;   // [qcap]
+    uint32_t mask;               // slots - 1 (power of two); 0 = table mode off (candidates go to the sort buffer)
+    uint32_t qcap;
+    uint32_t min_copies;
+    int bshift;                  // bucket of a key = key >> bshift
+};
 
 __host__ __device__ inline unsigned int div_up(unsigned long long a, unsigned long long b) {
     return (unsigned int)((a + b - 1) / b);
@@ -97,8 +116,10 @@ void launch_parse_segment(const LaunchCtx &lc, const SegDesc &sd, unsigned long 
 // words of the FASTQ per-tile arrays for segments of up to max_tiles tiles; *tile_cap = padded entries per array
 size_t parse_tile_array_words(size_t max_tiles, size_t *tile_cap);
 // ps_slot: ParseState slot holding this segment's n_zbuf (= (serial + 1) & 1)
+// ct.mask != 0: candidates are inserted into the count table instead of being appended to cand
 void launch_hash_segment(const LaunchCtx &lc, int k, const uint8_t *Z, uint32_t max_zbuf, int ps_slot, JobDev *jd,
-                         unsigned long long *cand, unsigned long long cand_cap, uint32_t seed, int use64);
+                         unsigned long long *cand, unsigned long long cand_cap, uint32_t seed, int use64,
+                         const CountTable &ct);
 
 struct SelectBufs {
     unsigned long long *keys_a, *keys_b;  // candidate buffer (keys_a) and its ping-pong partner
@@ -121,6 +142,19 @@ void launch_finalize(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, int 
 // sort (hash,count) pairs, sum equal hashes, keep count >= m; result in keys_a/vals_a, n in jd->n_unique
 void launch_merge_counts(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, uint64_t n, int min_copies);
 
+// ---- count-table mode (ac_select.cu)
+// tau <- upper edge of the histogram bucket holding the s-th smallest qualified key (if there are s);
+// jd->n_qualified <- qualified keys <= tau (all of them when fewer than s exist)
+void launch_table_tau_update(const LaunchCtx &lc, const CountTable &ct, JobDev *jd, int sketch_size);
+// qualified keys <= tau with their counts -> (keys_a, vals_a), n in jd->n_out
+void launch_table_collect(const LaunchCtx &lc, const CountTable &ct, const SelectBufs &sb, JobDev *jd, uint32_t n_qlist);
+// every key <= tau with its count -> (keys_a, vals_a), n in jd->n_out  (multi-GPU exchange needs unqualified ones too)
+void launch_table_export(const LaunchCtx &lc, const CountTable &ct, const SelectBufs &sb, JobDev *jd);
+// sort n (hash,count) pairs of (keys_a, vals_a); all n -> (tab_hash, tab_cnt); first min(n_q, s) -> sketch unless
+// all_entries (the pairs then include unqualified keys); sets n_sketch / n_qualified (= n_q) / n_table (= n)
+void launch_table_finish(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, uint32_t n, uint32_t n_q, int key_bits,
+                         int sketch_size, int all_entries);
+
 constexpr int MAX_RANGES = 64;  // hash ranges (= ranks) of the multi-GPU exchange
 struct RangeBounds {             // passed by value
     unsigned long long b[MAX_RANGES];  // b[r] = first hash owned by range r
@@ -141,6 +175,35 @@ double run_int_peak(const LaunchCtx &lc);
 
 #if defined(__CUDACC__)
 constexpr unsigned FULL = 0xffffffffu;
+
+// One occurrence of hash h (<= tau < CT_EMPTY) into the count table.  Linear probing from the low bits of h
+// (MurmurHash3 output: uniform).  A slot's key changes once, from empty to its owner, so an uncached read
+// that shows a foreign key is final and one that shows "empty" is settled by the CAS.
+__device__ __forceinline__ void ct_insert(const CountTable &ct, unsigned long long h, JobDev *jd) {
+    uint32_t slot = (uint32_t)h & ct.mask;
+    for (int probe = 0; probe < CT_MAX_PROBE; probe++, slot = (slot + 1u) & ct.mask) {
+        unsigned long long cur = __ldcg(ct.key + slot);
+        if (cur == CT_EMPTY) cur = atomicCAS(ct.key + slot, CT_EMPTY, h);
+        if (cur == CT_EMPTY || cur == h) {
+            const uint32_t c = atomicAdd(ct.cnt + slot, 1u) + 1u;
+            if (c == ct.min_copies) {   // the key qualifies now (exactly once per key)
+                atomicAdd(ct.qhist + (uint32_t)(h >> ct.bshift), 1u);
+                const uint32_t i = atomicAdd(&jd->n_qlist, 1u);
+                if (i < ct.qcap) ct.qlist[i] = h; else jd->overflow = 1u;
+            }
+            return;
+        }
+    }
+    jd->overflow = 1u;   // table (nearly) full: the pass is repeated through the sort path
+}
+// count of a key that is known to be in the table
+__device__ __forceinline__ uint32_t ct_lookup(const CountTable &ct, unsigned long long h) {
+    uint32_t slot = (uint32_t)h & ct.mask;
+    for (int probe = 0; probe < CT_MAX_PROBE; probe++, slot = (slot + 1u) & ct.mask)
+        if (__ldcg(ct.key + slot) == h) return __ldcg(ct.cnt + slot);
+    return 0u;
+}
+
 // exclusive sum scan over the CTA (NT threads, NT/32 <= 32 warps); total returned to all
 template <int NT>
 __device__ __forceinline__ uint32_t block_excl_sum(uint32_t v, uint32_t *s_w /*[33]*/, uint32_t &total) {

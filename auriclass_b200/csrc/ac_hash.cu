@@ -28,46 +28,63 @@ namespace ac {
 
 namespace {
 
-// staging full (tau close to max): opportunistic warp-aggregated append straight to the candidate buffer
-__device__ __noinline__ void cand_append_global(unsigned long long h, unsigned long long *cand,
-                                                unsigned long long *cand_count, unsigned long long cand_cap,
-                                                uint32_t *overflow) {
-    const unsigned act = __activemask();
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(act) - 1;
-    unsigned long long base = 0;
-    if (lane == leader) base = atomicAdd(cand_count, (unsigned long long)__popc(act));
-    base = __shfl_sync(act, base, leader);
-    const unsigned long long g = base + __popc(act & ((1u << lane) - 1u));
-    if (g < cand_cap) cand[g] = h; else *overflow = 1u;
-}
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <bool USE64>
-struct CandSink {
+// Where candidates go.  Lives in shared memory so that the hot loop carries no kernel parameters
+// (ptxas otherwise hoists their constant-bank loads in front of every window's threshold branch).
+struct SinkShared {
     unsigned long long tau;
-    uint32_t tau_top;              // high word of tau (64-bit hashes) / tau itself (32-bit hashes)
-    unsigned long long *s_buf;
-    uint32_t *s_cnt;
     unsigned long long *cand;
     unsigned long long *cand_count;
     unsigned long long cand_cap;
     uint32_t *overflow;
-    __device__ __forceinline__ void operator()(uint32_t vbits, uint32_t bit, uint64_t h1) {
-        // first look at the high word only (one compare for the common reject); 32-bit mode keeps the low word
-        const uint32_t top = USE64 ? (uint32_t)(h1 >> 32) : (uint32_t)h1;
-        if (top <= tau_top) {              // rare: tau is a small fraction of the hash space
-            const unsigned long long h = USE64 ? h1 : (h1 & 0xffffffffULL);  // Mash: 32-bit hashes for k <= 16
-            if (h <= tau && (vbits & bit)) {   // windows touching an invalid byte are dropped here
-                const uint32_t idx = atomicAdd(s_cnt, 1u);
-                if (idx < (uint32_t)K2_STAGE) s_buf[idx] = h;
-                else cand_append_global(h, cand, cand_count, cand_cap, overflow);
-            }
-        }
+    JobDev *jd;
+    CountTable ct;                         // ct.mask != 0: candidates go into the count table
+    uint32_t cnt;                          // staged candidates of this CTA (may exceed K2_STAGE: the excess went to global)
+    unsigned long long buf[K2_STAGE];
+};
+
+// staging full (tau close to max): opportunistic warp-aggregated append straight to the candidate buffer
+__device__ __noinline__ void cand_append_global(unsigned long long h, SinkShared *ss) {
+    if (ss->ct.mask) { ct_insert(ss->ct, h, ss->jd); return; }
+    const unsigned act = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(act) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(ss->cand_count, (unsigned long long)__popc(act));
+    base = __shfl_sync(act, base, leader);
+    const unsigned long long g = base + __popc(act & ((1u << lane) - 1u));
+    if (g < ss->cand_cap) ss->cand[g] = h; else *ss->overflow = 1u;
+}
+
+// rare path (about 1 window in 100 gets here, 1 in 2 of those is kept): finish the hash, exact test, stage
+template <bool USE64>
+__device__ __noinline__ void cand_stage(uint64_t p1, uint64_t p2, uint32_t window_ok, SinkShared *ss) {
+    if (!window_ok) return;            // windows touching an invalid byte are dropped here
+    const uint64_t h1 = ackmer::murmur3_close(p1, p2);
+    const unsigned long long h = USE64 ? h1 : (h1 & 0xffffffffULL);  // Mash: 32-bit hashes for k <= 16
+    if (h > ss->tau) return;
+    uint32_t idx;   // plain shared atomic: one lane at a time gets here, warp aggregation would cost more than it saves
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(idx) : "r"(smem_u32(&ss->cnt)) : "memory");
+    if (idx < (uint32_t)K2_STAGE) ss->buf[idx] = h;
+    else cand_append_global(h, ss);
+}
+
+template <bool USE64>
+struct CandSink {
+    uint32_t gate;   // 64-bit hashes: high word of tau, + 1 (saturating); 32-bit hashes: tau
+    SinkShared *ss;
+    __device__ __forceinline__ void operator()(uint32_t vbits, uint32_t bit, uint64_t p1, uint64_t p2) {
+        // Reject on the high words alone: hi(h) = hi(p1) + hi(p2) + carry, carry in {0, 1}, so
+        // hi(h) <= hi(tau) implies t <= hi(tau) or t == 2^32 - 1 for t = hi(p1) + hi(p2), i.e. t + 1 <= gate (mod 2^32).
+        bool maybe;
+        if constexpr (USE64) maybe = (uint32_t)(p1 >> 32) + (uint32_t)(p2 >> 32) + 1u <= gate;
+        else maybe = ((uint32_t)p1 ^ (uint32_t)(p1 >> 33)) + ((uint32_t)p2 ^ (uint32_t)(p2 >> 33)) <= gate;
+        if (maybe) cand_stage<USE64>(p1, p2, vbits & bit, ss);
     }
 };
 
 // ---- TMA (1-D bulk copy) + mbarrier helpers: sm_90+ PTX, UBLKCP in SASS
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // make the init visible to the async proxy
@@ -93,7 +110,8 @@ template <int K> struct K2MaxGroups { static constexpr int value = K2_TILE / (K 
 template <int K>
 __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t *__restrict__ Z, JobDev *__restrict__ jd,
                                                          unsigned long long *__restrict__ cand,
-                                                         unsigned long long cand_cap, uint32_t seed, int ps_slot) {
+                                                         unsigned long long cand_cap, uint32_t seed, int ps_slot,
+                                                         const CountTable ct) {
     using Q = ackmer::QuadCfg<K>;
     __shared__ __align__(128) uint8_t s_fwd[K2_TB + 64];  // base stream bytes of the tile (TMA destination)
     __shared__ __align__(16) uint8_t s_rc[K2_TB + 64];    // reverse complement of the tile: s_rc[p'] = comp(s_fwd[TB-1-p'])
@@ -104,8 +122,7 @@ __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t 
     __shared__ uint16_t s_groups[K2_MAXG];                // start positions of the groups of <= 32 consecutive valid windows
     __shared__ uint32_t s_ngroups;
     __shared__ uint32_t s_scan[33];
-    __shared__ unsigned long long s_buf[K2_STAGE];
-    __shared__ uint32_t s_cnt;
+    __shared__ SinkShared s_sink;
     __shared__ unsigned long long s_base;
     __shared__ unsigned long long s_stat[5];  // kmers, records, kept, short_len, bases
     __shared__ __align__(8) uint64_t s_bar;
@@ -118,7 +135,10 @@ __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t 
     if (tile_start >= n_win) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        s_cnt = 0; s_ngroups = 0; s_wv[K2_NWV] = 0;
+        s_ngroups = 0; s_wv[K2_NWV] = 0;
+        s_sink.cnt = 0; s_sink.tau = jd->tau;
+        s_sink.cand = cand; s_sink.cand_count = &jd->cand_count; s_sink.cand_cap = cand_cap;
+        s_sink.overflow = &jd->overflow; s_sink.jd = jd; s_sink.ct = ct;
         mbar_init(&s_bar, 1);
     }
     if (tid < 5) s_stat[tid] = 0;
@@ -195,11 +215,13 @@ __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t 
     if (n_groups > (uint32_t)K2_MAXG) __trap();  // cannot happen (see K2MaxGroups)
 
     CandSink<(K > 16)> sink;
-    sink.tau = jd->tau;
-    sink.tau_top = (K > 16) ? (uint32_t)(sink.tau >> 32) : (uint32_t)sink.tau;
-    sink.s_buf = s_buf; sink.s_cnt = &s_cnt;
-    sink.cand = cand; sink.cand_count = &jd->cand_count; sink.cand_cap = cand_cap;
-    sink.overflow = &jd->overflow;
+    {
+        const unsigned long long tau = s_sink.tau;
+        const uint32_t top = (uint32_t)(tau >> 32);
+        sink.gate = (K > 16) ? (top == 0xffffffffu ? top : top + 1u) : (uint32_t)tau;
+        sink.ss = &s_sink;
+    }
+    const ackmer::MurmurConsts mc;   // (registers are too scarce to hide these from ptxas' constant folding: 64/thread at 4 CTAs/SM)
 
     // ---- hash: a quad per group, lane c takes windows g+c+4j
     {
@@ -222,7 +244,7 @@ __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t 
 #pragma unroll
             for (int i = 0; i < Q::NL; i++) in[i] = rc_w[(QL >> 2) + i];
             ackmer::preshift<Q::NS>(in, QL & 3u, rw);
-            ackmer::process_quad_windows<K, 0>(fw, rw, vb, seed, sink);
+            ackmer::process_quad_windows<K, 0>(fw, rw, vb, seed, mc, sink);
         }
     }
 
@@ -261,38 +283,43 @@ __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t 
         if (n_bases) atomicAdd(&s_stat[4], (unsigned long long)n_bases);
     }
     __syncthreads();
-    const uint32_t n_staged = min(s_cnt, (uint32_t)K2_STAGE);
+    const uint32_t n_emitted = s_sink.cnt, n_staged = min(n_emitted, (uint32_t)K2_STAGE);
     if (tid == 0) {
         if (s_stat[0]) atomicAdd(&jd->n_kmers, s_stat[0]);
         if (s_stat[1]) atomicAdd(&jd->n_records, s_stat[1]);
         if (s_stat[2]) atomicAdd(&jd->n_kept, s_stat[2]);
         if (s_stat[3]) atomicAdd(&jd->n_short_len, s_stat[3]);
         if (s_stat[4]) atomicAdd(&jd->n_bases, s_stat[4]);
-        if (s_cnt) atomicAdd(&jd->cand_total, (unsigned long long)s_cnt);
-        s_base = n_staged ? atomicAdd(&jd->cand_count, (unsigned long long)n_staged) : 0ULL;
+        if (n_emitted) atomicAdd(&jd->cand_total, (unsigned long long)n_emitted);
+        s_base = (n_staged && !ct.mask) ? atomicAdd(&jd->cand_count, (unsigned long long)n_staged) : 0ULL;
+    }
+    if (ct.mask) {   // count-table mode: one insertion per staged candidate, the whole CTA in parallel
+        for (uint32_t i = tid; i < n_staged; i += K2_THREADS) ct_insert(ct, s_sink.buf[i], jd);
+        return;
     }
     __syncthreads();
     const unsigned long long base = s_base;
     for (uint32_t i = tid; i < n_staged; i += K2_THREADS) {
         const unsigned long long g = base + i;
-        if (g < cand_cap) cand[g] = s_buf[i]; else jd->overflow = 1u;
+        if (g < cand_cap) cand[g] = s_sink.buf[i]; else jd->overflow = 1u;
     }
 }
 
 template <int K>
 void launch_k(const LaunchCtx &lc, const uint8_t *Z, uint32_t max_zbuf, int ps_slot, JobDev *jd, unsigned long long *cand,
-              unsigned long long cand_cap, uint32_t seed) {
+              unsigned long long cand_cap, uint32_t seed, const CountTable &ct) {
     const unsigned grid = div_up(max_zbuf, K2_TILE);
-    k2_hash<K><<<grid, K2_THREADS, 0, lc.stream>>>(Z, jd, cand, cand_cap, seed, ps_slot);
+    k2_hash<K><<<grid, K2_THREADS, 0, lc.stream>>>(Z, jd, cand, cand_cap, seed, ps_slot, ct);
     ++*lc.launches;
 }
 
 }  // namespace
 
-#define AC_K_CASE(KK) case KK: launch_k<KK>(lc, Z, max_zbuf, ps_slot, jd, cand, cand_cap, seed); break;
+#define AC_K_CASE(KK) case KK: launch_k<KK>(lc, Z, max_zbuf, ps_slot, jd, cand, cand_cap, seed, ct); break;
 
 void launch_hash_segment(const LaunchCtx &lc, int k, const uint8_t *Z, uint32_t max_zbuf, int ps_slot, JobDev *jd,
-                         unsigned long long *cand, unsigned long long cand_cap, uint32_t seed, int use64) {
+                         unsigned long long *cand, unsigned long long cand_cap, uint32_t seed, int use64,
+                         const CountTable &ct) {
     (void)use64;  // the hash width follows k (CandSink<(K > 16)>)
     switch (k) {
 #ifdef AC_ONLY_K27  // development builds: one instantiation, seconds to compile

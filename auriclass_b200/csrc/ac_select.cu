@@ -335,6 +335,81 @@ __global__ void k3_table_ranges(const u64 *__restrict__ tab_hash, uint32_t n_tab
     out[r] = lo;
 }
 
+
+// ------------------------------------------------------- count-table mode
+// Threshold from the histogram of qualified keys: one CTA, thread t owns buckets [64t, 64t + 64).
+__global__ void __launch_bounds__(1024) k3t_tau_update(const uint32_t *__restrict__ qhist, JobDev *__restrict__ jd,
+                                                       uint32_t sketch_size, int bshift) {
+    __shared__ uint32_t s_w[33];
+    constexpr int PER = (1 << CT_BUCKET_BITS) / 1024;
+    const uint32_t t = threadIdx.x;
+    uint32_t mine = 0;
+    const uint4 *row = reinterpret_cast<const uint4 *>(qhist + (size_t)t * PER);
+#pragma unroll
+    for (int i = 0; i < PER / 4; i++) { const uint4 v = __ldcg(row + i); mine += v.x + v.y + v.z + v.w; }
+    uint32_t total;
+    const uint32_t before = block_excl_sum<1024>(mine, s_w, total);
+    if (t == 0) {
+        jd->n_out = 0;
+        if (total < sketch_size) { jd->n_qualified = total; jd->n_sketch = total; }
+    }
+    if (total >= sketch_size && before < sketch_size && before + mine >= sketch_size) {
+        uint32_t cum = before;
+        for (int i = 0; i < PER; i++) {
+            cum += __ldcg(qhist + (size_t)t * PER + i);
+            if (cum >= sketch_size) {
+                const u64 edge = (((u64)t * PER + i + 1) << bshift) - 1ULL;   // last key of the bucket
+                if (edge < jd->tau) jd->tau = edge;
+                jd->n_qualified = cum;
+                jd->n_sketch = sketch_size;
+                break;
+            }
+        }
+    }
+}
+
+// qualified keys <= tau, with their exact counts -> (keys, vals) in any order
+__global__ void __launch_bounds__(256) k3t_collect(const CountTable ct, uint32_t n_qlist, JobDev *__restrict__ jd,
+                                                   u64 *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t cap) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_qlist) return;
+    const u64 h = ct.qlist[i];
+    if (h > jd->tau) return;
+    const uint32_t c = ct_lookup(ct, h);
+    const uint32_t pos = atomicAdd(&jd->n_out, 1u);
+    if (pos < cap) { keys[pos] = h; vals[pos] = c; }
+}
+
+// every key <= tau with its count (multi-GPU exchange: counts below min_copies still add up across ranks)
+__global__ void __launch_bounds__(256) k3t_export(const CountTable ct, JobDev *__restrict__ jd, u64 *__restrict__ keys,
+                                                  uint32_t *__restrict__ vals, uint32_t cap) {
+    const uint32_t tau_stride = gridDim.x * blockDim.x;
+    const u64 tau = jd->tau;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot <= ct.mask; slot += tau_stride) {
+        const u64 h = __ldcg(ct.key + slot);
+        if (h != CT_EMPTY && h <= tau) {
+            const uint32_t pos = atomicAdd(&jd->n_out, 1u);
+            if (pos < cap) { keys[pos] = h; vals[pos] = __ldcg(ct.cnt + slot); }
+        }
+        if (slot + tau_stride < slot) break;   // 32-bit wrap (mask = 2^32 - 1 is not used, but stay safe)
+    }
+}
+
+// sorted pairs -> table (all n) and sketch (first n_sk); job counters
+__global__ void __launch_bounds__(256) k3t_finish(const u64 *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n,
+                                                  uint32_t n_sk, uint32_t n_q, uint32_t n_sketch, u64 *__restrict__ tab_hash,
+                                                  uint32_t *__restrict__ tab_cnt, u64 *__restrict__ sk_hash,
+                                                  uint32_t *__restrict__ sk_cnt, JobDev *__restrict__ jd) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const u64 k = keys[i];
+        const uint32_t v = vals[i];
+        tab_hash[i] = k; tab_cnt[i] = v;
+        if (i < n_sk) { sk_hash[i] = k; sk_cnt[i] = v; }
+    }
+    if (i == 0) { jd->n_table = n; jd->n_unique = n; jd->n_qualified = n_q; jd->n_sketch = n_sketch; jd->cand_count = 0; }
+}
+
 void runs_and_qualify(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, const u64 *keys, const uint32_t *vals,
                       uint32_t n, int sketch_size, int min_copies, u64 *out_hash, uint32_t *out_cnt, int compact) {
     const uint32_t n_tiles = div_up(n ? n : 1, SC_TILE);
@@ -362,6 +437,35 @@ void launch_consolidate(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, u
     const u64 *keys = where ? sb.keys_b : sb.keys_a;
     const uint32_t *vals = where ? sb.vals_b : sb.vals_a;
     runs_and_qualify(lc, sb, jd, keys, vals, n, sketch_size, min_copies, sb.sk_hash, sb.sk_cnt, 0);
+}
+
+void launch_table_tau_update(const LaunchCtx &lc, const CountTable &ct, JobDev *jd, int sketch_size) {
+    k3t_tau_update<<<1, 1024, 0, lc.stream>>>(ct.qhist, jd, (uint32_t)sketch_size, ct.bshift);
+    ++*lc.launches;
+}
+
+void launch_table_collect(const LaunchCtx &lc, const CountTable &ct, const SelectBufs &sb, JobDev *jd, uint32_t n_qlist) {
+    if (!n_qlist) return;
+    k3t_collect<<<div_up(n_qlist, 256), 256, 0, lc.stream>>>(ct, n_qlist, jd, sb.keys_a, sb.vals_a, (uint32_t)sb.cap);
+    ++*lc.launches;
+}
+
+void launch_table_export(const LaunchCtx &lc, const CountTable &ct, const SelectBufs &sb, JobDev *jd) {
+    k3t_export<<<148 * 8, 256, 0, lc.stream>>>(ct, jd, sb.keys_a, sb.vals_a, (uint32_t)sb.cap);
+    ++*lc.launches;
+}
+
+void launch_table_finish(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, uint32_t n, uint32_t n_q, int key_bits,
+                         int sketch_size, int all_entries) {
+    const int where = radix_sort_pairs(lc, sb.keys_a, sb.vals_a, sb.keys_b, sb.vals_b, n, key_bits, sb.hist,
+                                       sb.hist + (size_t)256 * div_up(n ? n : 1, RS_TILE));
+    const u64 *keys = where ? sb.keys_b : sb.keys_a;
+    const uint32_t *vals = where ? sb.vals_b : sb.vals_a;
+    const uint32_t n_sk = n_q < (uint32_t)sketch_size ? n_q : (uint32_t)sketch_size;
+    // all_entries: the pairs include unqualified keys (exchange table), so there is no sketch prefix to copy
+    k3t_finish<<<div_up(n ? n : 1, 256), 256, 0, lc.stream>>>(keys, vals, n, all_entries ? 0u : n_sk, n_q, n_sk, sb.tab_hash,
+                                                              sb.tab_cnt, sb.sk_hash, sb.sk_cnt, jd);
+    ++*lc.launches;
 }
 
 void launch_finalize(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, int use64) {

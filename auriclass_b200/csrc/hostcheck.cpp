@@ -50,7 +50,8 @@ long run_k(const uint8_t *z, size_t n, uint64_t *out, size_t cap) {
 struct CollectPos {
     std::vector<std::pair<uint64_t, uint64_t>> *out;
     uint64_t base;  // stream position of the lane's window 0
-    void operator()(uint32_t vb, uint32_t bit, uint64_t h) {
+    void operator()(uint32_t vb, uint32_t bit, uint64_t p1, uint64_t p2) {
+        const uint64_t h = ackmer::murmur3_close(p1, p2);
         if (vb & bit) { int j = 0; while (!((bit >> (4 * j)) & 1u)) j++; out->push_back({base + 4 * (uint64_t)j, h}); }
     }
 };
@@ -89,7 +90,8 @@ long run_quad_k(const uint8_t *z, size_t n, uint64_t *out, size_t cap) {
             memcpy(in, &rc[QL & ~(size_t)3], sizeof(in));
             ackmer::preshift<Q::NS>(in, (uint32_t)(QL & 3), rw);
             CollectPos col{&hs, (uint64_t)A};
-            ackmer::process_quad_windows<K, 0>(fw, rw, vb, 42u, col);
+            const ackmer::MurmurConsts mc;
+            ackmer::process_quad_windows<K, 0>(fw, rw, vb, 42u, mc, col);
         }
     }
     std::sort(hs.begin(), hs.end());

@@ -94,11 +94,44 @@ AC_HD uint32_t key_word(const uint32_t *w) {
     if constexpr (J < (K + 3) / 4) return w[J]; else return 0u;
 }
 
-// h1 of MurmurHash3_x64_128(key, K, seed).  w[] = the K key bytes as (K+3)/4
-// little-endian words, bytes past K in the last word MUST be zero.
-// Mash: hash = first 8 bytes of the 128-bit digest = h1.
+// h * 5 + c (mod 2^64) with c held in a register pair by the caller: IMAD.WIDE + IMAD on the device
+// (nvcc's own expansion materialises c with two moves and adds the high product separately)
+AC_HD uint64_t mul5_add(uint64_t h, uint64_t c) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+    uint64_t p;
+    uint32_t ph;
+    asm("mad.wide.u32 %0, %1, 5, %2;" : "=l"(p) : "r"(lo), "l"(c));
+    ph = (uint32_t)(p >> 32);
+    asm("mad.lo.u32 %0, %1, 5, %0;" : "+r"(ph) : "r"(hi));
+    return ((uint64_t)ph << 32) | (uint32_t)p;
+#else
+    return h * 5 + c;
+#endif
+}
+
+// the two additive constants of the MurmurHash3 block step (a kernel keeps them in registers)
+struct MurmurConsts {
+    uint64_t a, b;
+    AC_HD MurmurConsts() : a(0x52dce729ULL), b(0x38495ab5ULL) {}
+};
+
+// fmix64 without its last `x ^= x >> 33`: that step only changes the low word
+AC_HD uint64_t fmix64_open(uint64_t x) {
+    x ^= x >> 33; x = mul64(x, 0xff51afd7ed558ccdULL);
+    x ^= x >> 33; x = mul64(x, 0xc4ceb9fe1a85ec53ULL);
+    return x;
+}
+// h1 of the digest from the two open fmix products: fmix(h1) + fmix(h2)
+AC_HD uint64_t murmur3_close(uint64_t p1, uint64_t p2) {
+    return (p1 ^ (p1 >> 33)) + (p2 ^ (p2 >> 33));
+}
+
+// MurmurHash3_x64_128(key, K, seed) up to the open fmix products (p1, p2); h1 of the digest =
+// murmur3_close(p1, p2).  w[] = the K key bytes as (K+3)/4 little-endian words, bytes past K in the
+// last word MUST be zero.  Mash: hash = first 8 bytes of the 128-bit digest = h1.
 template <int K>
-AC_HD uint64_t murmur3_h1(const uint32_t *w, uint32_t seed) {
+AC_HD void murmur3_open(const uint32_t *w, uint32_t seed, const MurmurConsts &mc, uint64_t &p1, uint64_t &p2) {
     const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
     uint64_t h1 = seed, h2 = seed;
     constexpr int NB = K / 16;
@@ -106,17 +139,17 @@ AC_HD uint64_t murmur3_h1(const uint32_t *w, uint32_t seed) {
         uint64_t k1 = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
         uint64_t k2 = (uint64_t)w[2] | ((uint64_t)w[3] << 32);
         k1 = mul64(k1, c1); k1 = rotl64<31>(k1); k1 = mul64(k1, c2); h1 ^= k1;
-        h1 = rotl64<27>(h1); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+        h1 = rotl64<27>(h1); h1 += h2; h1 = mul5_add(h1, mc.a);
         k2 = mul64(k2, c2); k2 = rotl64<33>(k2); k2 = mul64(k2, c1); h2 ^= k2;
-        h2 = rotl64<31>(h2); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+        h2 = rotl64<31>(h2); h2 += h1; h2 = mul5_add(h2, mc.b);
     }
     if constexpr (NB >= 2) {
         uint64_t k1 = (uint64_t)w[4] | ((uint64_t)w[5] << 32);
         uint64_t k2 = (uint64_t)w[6] | ((uint64_t)w[7] << 32);
         k1 = mul64(k1, c1); k1 = rotl64<31>(k1); k1 = mul64(k1, c2); h1 ^= k1;
-        h1 = rotl64<27>(h1); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+        h1 = rotl64<27>(h1); h1 += h2; h1 = mul5_add(h1, mc.a);
         k2 = mul64(k2, c2); k2 = rotl64<33>(k2); k2 = mul64(k2, c1); h2 ^= k2;
-        h2 = rotl64<31>(h2); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+        h2 = rotl64<31>(h2); h2 += h1; h2 = mul5_add(h2, mc.b);
     }
     constexpr int T = K & 15;
     if constexpr (T > 8) {
@@ -129,9 +162,16 @@ AC_HD uint64_t murmur3_h1(const uint32_t *w, uint32_t seed) {
     }
     h1 ^= (uint64_t)K; h2 ^= (uint64_t)K;
     h1 += h2; h2 += h1;
-    h1 = fmix64(h1); h2 = fmix64(h2);
-    h1 += h2;
-    return h1;
+    p1 = fmix64_open(h1); p2 = fmix64_open(h2);
+}
+
+// h1 of MurmurHash3_x64_128(key, K, seed)
+template <int K>
+AC_HD uint64_t murmur3_h1(const uint32_t *w, uint32_t seed) {
+    const MurmurConsts mc;
+    uint64_t p1, p2;
+    murmur3_open<K>(w, seed, mc, p1, p2);
+    return murmur3_close(p1, p2);
 }
 
 // SWAR complement of four sanitised bases: A(41)<->T(54) differ by 0x15,
@@ -304,9 +344,12 @@ AC_HD void preshift(const uint32_t *in, uint32_t off, uint32_t *out) {
 }
 
 // fw / rw: the lane's pre-shifted forward / reverse-complement words (QuadCfg::NS each).
-// vbits: bit 4j set = the lane's window j may be emitted.  emit(vbits, 1 << 4j, h1) is called for every window.
+// vbits: bit 4j set = the lane's window j may be emitted.  emit(vbits, 1 << 4j, p1, p2) is called for every
+// window with the open fmix products: the hash is murmur3_close(p1, p2), which the caller only needs to
+// finish for the few windows whose high words can still pass its threshold.
 template <int K, int J, class Emit>
-AC_HD void process_quad_windows(const uint32_t *fw, const uint32_t *rw, uint32_t vbits, uint32_t seed, Emit &emit) {
+AC_HD void process_quad_windows(const uint32_t *fw, const uint32_t *rw, uint32_t vbits, uint32_t seed,
+                                const MurmurConsts &mc, Emit &emit) {
     using C = QuadCfg<K>;
     if constexpr (J < C::G) {
         uint32_t f[C::NW], c[C::NW];
@@ -333,8 +376,10 @@ AC_HD void process_quad_windows(const uint32_t *fw, const uint32_t *rw, uint32_t
 #pragma unroll
         for (int m = 0; m < C::NW; m++) key[m] = use_rc ? c[m] : f[m];
         key[C::NW - 1] &= last_mask;  // bytes past the k-mer in its last word are not part of the key
-        emit(vbits, 1u << (4 * J), murmur3_h1<K>(key, seed));
-        process_quad_windows<K, J + 1, Emit>(fw, rw, vbits, seed, emit);
+        uint64_t p1, p2;
+        murmur3_open<K>(key, seed, mc, p1, p2);
+        emit(vbits, 1u << (4 * J), p1, p2);
+        process_quad_windows<K, J + 1, Emit>(fw, rw, vbits, seed, mc, emit);
     }
 }
 

@@ -301,6 +301,54 @@ def test_speculation_failure_falls_back_exactly(engine):
     assert sk.info["passes"] == 2
 
 
+def test_count_table_overflow_falls_back_to_sorting():
+    """AC_TABLE_LOG2=10: the speculative pass's count table (1,024 slots) fills up, the pass is void and
+    is repeated through the sort path with the same threshold -- same sketch, two passes."""
+    import os
+    from auriclass_b200.mash_gpu import MashGPU
+    os.environ["AC_TABLE_LOG2"] = "10"
+    try:
+        eng = MashGPU(0)
+    finally:
+        del os.environ["AC_TABLE_LOG2"]
+    try:
+        contigs = synth.genome(seed=17, scale=0.02)
+        fq = synth.fastq_reads(contigs, 60_000, seed=18).tobytes()   # ~19 MB: speculative
+        sk = eng.sketch_bytes([fq], k=27, s=2000, m=3, chunk=5 << 20)
+        assert_same_sketch(sk, oracle.sketch_parallel([fq], 27, 2000, 3))
+        assert sk.info["passes"] == 2
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("k,s,m", [(27, 50000, 1), (21, 10000, 1), (16, 5000, 1)])
+def test_fasta_full_genome_through_count_table(engine, k, s, m):
+    """C1-sized assembly (12.4 Mb, 7 contigs): large enough for the speculative threshold, so the sketch
+    comes out of the count table with min_copies = 1 (k = 16: 32-bit hashes, 28-bit bucket space)."""
+    fa = synth.fasta_bytes(synth.genome(seed=20240001))
+    sk = engine.sketch_bytes([fa], k=k, s=s, m=m, mode=AC_MODE_FASTA)
+    assert_same_sketch(sk, oracle.sketch_parallel([fa], k, s, m))
+    assert sk.info["passes"] == 1 and sk.info["n_candidates"] < sk.info["n_kmers"] // 8
+
+
+def test_reads_with_duplicated_low_complexity_records(engine):
+    """Thousands of identical low-complexity reads: one hash occurs in every window of whole tiles, so K2's
+    shared-memory staging overflows and the excess goes straight into the count table."""
+    contigs = synth.genome(seed=31, scale=0.05)
+    fq = synth.fastq_reads(contigs, 30_000, seed=32).tobytes()
+    # a repeat unit whose k-mers include one below the speculative threshold (2^60), found with the oracle
+    unit = next(u for u in (b"A", b"C", b"AC", b"AG", b"AT", b"CG", b"AAC", b"AAG", b"AAT", b"ACC", b"ACG", b"AGC", b"AACT")
+                if oracle.all_hashes(b">r\n" + (u * 60)[:60] + b"\n", 27).min() < (1 << 60))
+    seq = (unit * 150)[:150]
+    poly = b"".join(b"@p%d\n%s\n+\n%s\n" % (i, seq, b"I" * 150) for i in range(6000))
+    mono = b"".join(b"@q%d\n%s\n+\n%s\n" % (i, b"ACGT" * 37, b"I" * 148) for i in range(3000))
+    cut = fq.rfind(b"\n@SYN", 0, len(fq) // 2) + 1
+    buf = fq[:cut] + poly + mono + fq[cut:]
+    ref = oracle.sketch_parallel([buf], 27, 3000, 3)
+    sk = engine.sketch_bytes([buf], k=27, s=3000, m=3, chunk=7 << 20)
+    assert_same_sketch(sk, ref)
+
+
 def test_fasta_genome_scale(engine):
     contigs = synth.genome(seed=3, scale=0.25)
     fa = synth.fasta_bytes(contigs)
@@ -421,6 +469,44 @@ def test_sharded_cuda_backend_emulated_ranks(engine, reads, P, s, m):
     assert np.array_equal(h, ref.hashes) and np.array_equal(c, ref.counts)
     assert sk.genome_size == ref.genome_size and sk.coverage == ref.coverage
     assert sum(t.counters[3] for _, t in tables) == ref.n_kmers
+
+
+def test_sharded_emulated_ranks_speculative_tables(engine):
+    """Shards big enough for the speculative pass: every rank's exchange table is exported from its count
+    table (all keys <= tau, unqualified ones included) -- the merged sketch equals the oracle's."""
+    import torch
+    from auriclass_b200.sharded import CudaTableBackend
+    be = CudaTableBackend(engine)
+    P, s, m = 2, 2000, 3
+    contigs = synth.genome(seed=41, scale=0.02)
+    fq = synth.fastq_reads(contigs, 50_000, seed=42).tobytes()   # ~16 MB -> two 8 MB shards
+    shards = _split_fastq(fq, P)
+
+    def job_for(buf):
+        job = engine._begin(27, s, 42, m, AC_MODE_READS)
+        a = np.frombuffer(buf, np.uint8)
+        _lib.check(engine.lib.ac_sketch_feed(job, a.ctypes.data, a.size, 0, 1))
+        return job
+
+    taus = [be.local_table(job_for(buf), lambda tau: tau, P)[1].tau for buf in shards]
+    assert max(taus) < (1 << 60)            # speculative thresholds held
+    tau_cut = min(taus)
+    tables = [be.local_table(job_for(buf), lambda tau: tau_cut, P) for buf in shards]
+    owned_h, owned_c = [], []
+    for r in range(P):
+        hs, cs = [], []
+        for splits, t in tables:
+            o = sum(splits[:r])
+            hs.append(t.hashes[o:o + splits[r]]); cs.append(t.counts[o:o + splits[r]])
+        h, c = torch.cat(hs).contiguous(), torch.cat(cs).contiguous()
+        n_q = be.merge_counts(h, c, m)
+        owned_h.append(h[:n_q]); owned_c.append(c[:n_q])
+    fh, fc = torch.cat(owned_h)[:s].contiguous(), torch.cat(owned_c)[:s].contiguous()
+    sk = be.build_sketch(fh, fc, 27, s, "emulated")
+    ref = oracle.sketch_parallel([fq], 27, s, m)
+    h, c = sk.hashes()
+    assert np.array_equal(h, ref.hashes) and np.array_equal(c, ref.counts)
+    assert sk.genome_size == ref.genome_size and sk.coverage == ref.coverage
 
 
 def test_sharded_nccl_world1(engine, reads):

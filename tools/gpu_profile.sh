@@ -12,10 +12,10 @@ python bench.py $prof > gpurun_out/bench_prof_${tag}.json 2> gpurun_out/bench_pr
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_${tag}.csv \
     python bench.py $prof > gpurun_out/ncu_list_${tag}.log 2>&1
 echo "ncu list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:'k1_|k2_hash' -s 60 -c 6 \
+ncu --set full --clock-control none --import-source on -k regex:'k1q_|k1_fa|k2_hash' -s 80 -c 8 \
     -o gpurun_out/prof_${tag} -f python bench.py $prof > gpurun_out/ncu_full_${tag}.log 2>&1
 echo "ncu full rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:'rs_|k3_' -s 40 -c 16 \
+ncu --set full --clock-control none --import-source on -k regex:'rs_|k3' -s 20 -c 16 \
     -o gpurun_out/prof_sel_${tag} -f python bench.py $prof > gpurun_out/ncu_full_sel_${tag}.log 2>&1
 echo "ncu full sel rc=$?"
 ls -la gpurun_out
