@@ -25,7 +25,7 @@ class SketchInfo(C.Structure):
         ("total_len", C.c_uint64), ("n_kmers", C.c_uint64), ("n_candidates", C.c_uint64),
         ("max_hash", C.c_uint64), ("sum_counts", C.c_uint64), ("final_tau", C.c_uint64),
         ("genome_size", C.c_double), ("coverage", C.c_double),
-        ("hash_bits", C.c_int32), ("passes", C.c_int32),
+        ("hash_bits", C.c_int32), ("passes", C.c_int32), ("n_bases", C.c_uint64),
     ]
 
 
@@ -73,6 +73,7 @@ SIGNATURES = {
     "ac_refs_free": (None, [_vp]),
     "ac_dist": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ac_dist_batch": (C.c_int, [_vp, _vp, C.POINTER(_vp), C.c_int, _vp, _vp, _vp, _vp]),
+    "ac_dist_pairs": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "ac_launch_count": (C.c_uint64, [_vp]),
     "ac_set_profile": (C.c_int, [_vp, C.c_int]),
     "ac_last_job_times": (C.c_int, [_vp, C.POINTER(C.c_float * 4)]),

@@ -760,6 +760,7 @@ static void fill_info(const ac_job *j, const JobDev &h, ac_sketch_info *info) {
     info->coverage = h.coverage;
     info->hash_bits = j->use64 ? 64 : 32;
     info->passes = j->passes;
+    info->n_bases = h.n_bases;
 }
 
 // end of a count-table pass: final threshold, then the qualified keys <= tau (for_exchange: every key <= tau)
@@ -1129,6 +1130,30 @@ extern "C" int ac_dist_batch(ac_ctx *c, const ac_refs *refs, const ac_sketch *co
     if (pvalue) memcpy(pvalue, c->h_p, n_out * 8);
     if (common) memcpy(common, c->h_common, n_out * 8);
     if (denom) memcpy(denom, c->h_denom, n_out * 8);
+    return AC_OK;
+}
+
+extern "C" int ac_dist_pairs(ac_ctx *c, const ac_refs *a, int i0, int ni, const ac_refs *b, int j0, int nj, double *distance,
+                             double *pvalue, uint64_t *common, uint64_t *denom) {
+    if (!c || !a || !b) return fail(AC_E_PARAM, "ac_dist_pairs: NULL argument");
+    if (i0 < 0 || ni < 0 || j0 < 0 || nj < 0 || i0 + ni > a->n_refs || j0 + nj > b->n_refs)
+        return fail(AC_E_PARAM, "ac_dist_pairs: tile [%d,%d) x [%d,%d) outside %d x %d sketches", i0, i0 + ni, j0, j0 + nj, a->n_refs, b->n_refs);
+    if (a->k != b->k || a->hash_bits != b->hash_bits)
+        return fail(AC_E_PARAM_MISMATCH, "sketch sets disagree: k=%d/%d-bit vs k=%d/%d-bit", a->k, a->hash_bits, b->k, b->hash_bits);
+    CK(cudaSetDevice(c->dev));
+    const size_t n_out = (size_t)ni * (size_t)nj;
+    if (n_out == 0) return AC_OK;
+    int rc = ensure_dist(c, n_out, 1);
+    if (rc) return rc;
+    LaunchCtx lc{c->s_comp, &c->launches};
+    launch_dist_pairs(lc, a->d_hash, a->d_off, a->d_len, (uint32_t)i0, (uint32_t)ni, b->d_hash, b->d_off, b->d_len, (uint32_t)j0,
+                      (uint32_t)nj, a->k, (unsigned long long)std::min(a->s, b->s), c->d_dist, c->d_p, c->d_common, c->d_denom);
+    CK(cudaGetLastError());
+    if (distance) CK(cudaMemcpyAsync(distance, c->d_dist, n_out * 8, cudaMemcpyDeviceToHost, c->s_comp));
+    if (pvalue) CK(cudaMemcpyAsync(pvalue, c->d_p, n_out * 8, cudaMemcpyDeviceToHost, c->s_comp));
+    if (common) CK(cudaMemcpyAsync(common, c->d_common, n_out * 8, cudaMemcpyDeviceToHost, c->s_comp));
+    if (denom) CK(cudaMemcpyAsync(denom, c->d_denom, n_out * 8, cudaMemcpyDeviceToHost, c->s_comp));
+    CK(cudaStreamSynchronize(c->s_comp));
     return AC_OK;
 }
 

@@ -170,6 +170,13 @@ void launch_dist(const LaunchCtx &lc, const unsigned long long *ref_hashes, cons
                  unsigned long long sketch_size, unsigned long long max_q_n, double *d_dist, double *d_p,
                  unsigned long long *d_common, unsigned long long *d_denom);
 
+// tile of pairs: sketches [i0, i0+ni) of set A against [j0, j0+nj) of set B, outputs [ni][nj] row-major
+void launch_dist_pairs(const LaunchCtx &lc, const unsigned long long *a_hashes, const unsigned long long *a_off,
+                       const unsigned long long *a_len, uint32_t i0, uint32_t ni, const unsigned long long *b_hashes,
+                       const unsigned long long *b_off, const unsigned long long *b_len, uint32_t j0, uint32_t nj, int k,
+                       unsigned long long sketch_size, double *d_dist, double *d_p, unsigned long long *d_common,
+                       unsigned long long *d_denom);
+
 double run_int_peak(const LaunchCtx &lc);
 
 

@@ -168,6 +168,118 @@ __global__ void __launch_bounds__(D_THREADS) k5_dist(const u64 *__restrict__ ref
     }
 }
 
+
+// distance and p-value from the shared-hash count (App. A.6); one thread
+__device__ void d_finish_pair(u64 common, u64 denom, int k, u64 len_a, u64 len_b, double *o_dist, double *o_p) {
+    double d;
+    if (common == denom) d = 0.0;
+    else if (common == 0) d = 1.0;
+    else {
+        const double jac = (double)common / (double)denom;
+        d = -log(2.0 * jac / (1.0 + jac)) / k;
+    }
+    double pv;
+    if (common == 0) pv = 1.0;
+    else {
+        const double space = scalbn(1.0, 2 * k);  // 4^k, exact
+        const double pX = 1.0 / (1.0 + space / (double)len_a);
+        const double pY = 1.0 / (1.0 + space / (double)len_b);
+        const double r = pX * pY / (pX + pY - pX * pY);
+        pv = d_binomial_Q(common - 1, r, denom);
+    }
+    *o_dist = d; *o_p = pv;
+}
+
+// ---- K5 for tiles of pairs (all-vs-all `mash dist`, BASELINE config 5): merge path, one warp per pair.
+// The merged sequence of the two ascending lists (ties: the A element first, its B twin right behind it) is cut
+// into 32 equal diagonal ranges; a lane finds its start by binary search along the diagonal, walks its range
+// and counts distinct values and twins.  Mash's capped merge (App. A.6) stops at the S-th distinct value and
+// counts a twin of that value too, so: common = twins whose rank (distinct values up to and including their
+// A twin) is <= S, denom = min(S, distinct).  Only diagonals below 2S + 1 can matter.
+constexpr int P_WARPS = 8;   // pairs per CTA
+
+struct PathPos { uint32_t i, j; };
+
+__device__ __forceinline__ PathPos merge_path_split(const u64 *__restrict__ A, uint32_t nA, const u64 *__restrict__ B,
+                                                   uint32_t nB, uint32_t d) {
+    uint32_t lo = d > nB ? d - nB : 0u, hi = d < nA ? d : nA;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        // A[mid] <= B[d - mid - 1]: A[mid] is merged before that B element, the split lies further right
+        if (A[mid] <= B[d - mid - 1]) lo = mid + 1; else hi = mid;
+    }
+    return PathPos{lo, d - lo};
+}
+
+// walks items [pos, pos + len) of the merged sequence; returns distinct values, and twins whose rank
+// (rank_before + distinct values so far in this range) is <= S
+__device__ __forceinline__ void merge_walk(const u64 *__restrict__ A, uint32_t nA, const u64 *__restrict__ B, uint32_t nB,
+                                           PathPos p, uint32_t len, u64 rank_before, u64 S, uint32_t &distinct,
+                                           uint32_t &twins_in) {
+    uint32_t i = p.i, j = p.j, dist = 0, tw = 0;
+    u64 a = i < nA ? A[i] : ~0ULL, b = j < nB ? B[j] : ~0ULL;
+    u64 last_a = i > 0 ? A[i - 1] : 0ULL;
+    bool have_last = i > 0;
+    for (uint32_t t = 0; t < len; t++) {
+        const bool take_a = (j >= nB) || (i < nA && a <= b);
+        if (take_a) {
+            dist++;
+            last_a = a; have_last = true;
+            i++;
+            a = i < nA ? A[i] : ~0ULL;
+        } else {
+            if (have_last && b == last_a) { if (rank_before + dist <= S) tw++; }   // twin of the A element just merged
+            else dist++;
+            j++;
+            b = j < nB ? B[j] : ~0ULL;
+        }
+    }
+    distinct = dist; twins_in = tw;
+}
+
+__global__ void __launch_bounds__(P_WARPS * 32) k5_pairs(const u64 *__restrict__ a_hashes, const u64 *__restrict__ a_off,
+                                                         const u64 *__restrict__ a_len, uint32_t i0, uint32_t ni,
+                                                         const u64 *__restrict__ b_hashes, const u64 *__restrict__ b_off,
+                                                         const u64 *__restrict__ b_len, uint32_t j0, uint32_t nj, int k, u64 S,
+                                                         double *__restrict__ o_dist, double *__restrict__ o_p,
+                                                         u64 *__restrict__ o_common, u64 *__restrict__ o_denom) {
+    const uint32_t lane = threadIdx.x & 31;
+    const u64 pair = (u64)blockIdx.x * P_WARPS + (threadIdx.x >> 5);
+    if (pair >= (u64)ni * nj) return;
+    const uint32_t ia = i0 + (uint32_t)(pair / nj), jb = j0 + (uint32_t)(pair % nj);
+    const u64 *A = a_hashes + a_off[ia];
+    const uint32_t nA = (uint32_t)(a_off[ia + 1] - a_off[ia]);
+    const u64 *B = b_hashes + b_off[jb];
+    const uint32_t nB = (uint32_t)(b_off[jb + 1] - b_off[jb]);
+    const u64 total = (u64)nA + nB;
+    const uint32_t L = (uint32_t)(total < 2 * S + 1 ? total : 2 * S + 1);   // diagonals that can matter
+    const uint32_t per = (L + 31) / 32;
+    const uint32_t d0 = min(lane * per, L), d1 = min(d0 + per, L);
+    const PathPos p = merge_path_split(A, nA, B, nB, d0);
+    // pass 1: distinct values per lane (rank_before = 0 and S = max: every twin counts)
+    uint32_t distinct, twins_all;
+    merge_walk(A, nA, B, nB, p, d1 - d0, 0, ~0ULL, distinct, twins_all);
+    uint32_t inc = distinct;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += t;
+    }
+    const u64 before = inc - distinct;
+    const u64 uni = __shfl_sync(FULL, inc, 31);
+    // pass 2 only where the cap cuts through the lane's range
+    uint32_t twins_in;
+    if (before + distinct <= S) twins_in = twins_all;
+    else merge_walk(A, nA, B, nB, p, d1 - d0, before, S, distinct, twins_in);
+    const u64 common = __reduce_add_sync(FULL, twins_in);
+    if (lane == 0) {
+        // diagonals beyond L were not walked: then uni >= S already, so the cap decides
+        const u64 denom = uni < S ? uni : S;
+        d_finish_pair(common, denom, k, a_len[ia], b_len[jb], o_dist + pair, o_p + pair);
+        o_common[pair] = common; o_denom[pair] = denom;
+    }
+}
+
 // ---- integer issue peak: independent IMAD (fma pipe) + LOP3 (alu pipe) chains ----
 __global__ void __launch_bounds__(256) k_int_peak(uint32_t *out, int iters) {
     uint32_t a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -202,6 +314,18 @@ void launch_dist(const LaunchCtx &lc, const unsigned long long *ref_hashes, cons
     }
     k5_dist<<<n_refs * n_q, D_THREADS, smem, lc.stream>>>(ref_hashes, ref_off, ref_len, n_refs, q_hashes, q_n, q_len, k,
                                                        sketch_size, d_dist, d_p, d_common, d_denom);
+    ++*lc.launches;
+}
+
+void launch_dist_pairs(const LaunchCtx &lc, const unsigned long long *a_hashes, const unsigned long long *a_off,
+                       const unsigned long long *a_len, uint32_t i0, uint32_t ni, const unsigned long long *b_hashes,
+                       const unsigned long long *b_off, const unsigned long long *b_len, uint32_t j0, uint32_t nj, int k,
+                       unsigned long long sketch_size, double *d_dist, double *d_p, unsigned long long *d_common,
+                       unsigned long long *d_denom) {
+    const unsigned long long pairs = (unsigned long long)ni * nj;
+    if (!pairs) return;
+    k5_pairs<<<div_up(pairs, P_WARPS), P_WARPS * 32, 0, lc.stream>>>(a_hashes, a_off, a_len, i0, ni, b_hashes, b_off, b_len, j0,
+                                                                  nj, k, sketch_size, d_dist, d_p, d_common, d_denom);
     ++*lc.launches;
 }
 

@@ -12,7 +12,6 @@ from __future__ import annotations
 
 import ctypes as C
 import time
-import zlib
 from dataclasses import dataclass, field
 from pathlib import Path
 from typing import Iterable, List, Optional, Sequence, Tuple, Union
@@ -36,7 +35,8 @@ def fmt_g(x: float) -> str:
 class StreamStats:
     bytes_in: int = 0          # inflated bytes handed to the GPU
     read_s: float = 0.0        # file reads
-    inflate_s: float = 0.0     # gzip inflate (host, timed separately per north_star)
+    inflate_s: float = 0.0     # gzip inflate: thread-seconds inside zlib (host, timed separately per north_star)
+    inflate_wall_s: float = 0.0  # wall time the feeder waited for inflated bytes (what parallel inflate shrinks)
     feed_s: float = 0.0        # time inside ac_sketch_feed (enqueue + occasional sync)
     end_s: float = 0.0         # ac_sketch_end
     total_s: float = 0.0
@@ -141,6 +141,7 @@ class MashGPU:
         self.device = device
         self._pinned: List[int] = []
         self._refs_cache = {}
+        self.inflate_threads: Optional[int] = None   # None: inflate.default_threads()
 
     # ---------------------------------------------------------------- plumbing
     @property
@@ -204,64 +205,38 @@ class MashGPU:
         return job.value
 
     def _stream_file(self, job: int, path: PathLike, file_idx: int, st: StreamStats) -> None:
-        """Duty (2) of the host: file bytes -> (inflate) -> pinned buffer -> ac_sketch_feed."""
+        """Duty (2) of the host: file bytes -> (inflate, inflate.py) -> pinned buffer -> ac_sketch_feed."""
+        from . import inflate
         bufs = self._staging()
         which = 0
-        fed_since_wait = 0
-        with open(path, "rb") as f:
-            magic = f.read(2)
-            f.seek(0)
-            gz = magic == b"\x1f\x8b"
-            dec = zlib.decompressobj(wbits=47) if gz else None
-            pending = b""
-            eof = False
-            while not eof:
-                ptr, mv = bufs[which]
-                n = 0
-                if not gz:
-                    t0 = time.perf_counter()
-                    n = f.readinto(mv) or 0
-                    st.read_s += time.perf_counter() - t0
-                    eof = n < CHUNK_BYTES
-                else:
-                    while n < CHUNK_BYTES and not eof:
-                        if dec.unconsumed_tail:
-                            src = dec.unconsumed_tail
-                        elif dec.eof:
-                            # next gzip member (concatenated members are legal, App. A.2 S1)
-                            rest = dec.unused_data
-                            dec = zlib.decompressobj(wbits=47)
-                            src = rest
-                            if not src:
-                                t0 = time.perf_counter()
-                                src = f.read(1 << 20)
-                                st.read_s += time.perf_counter() - t0
-                                if not src:
-                                    eof = True
-                                    break
-                        else:
-                            t0 = time.perf_counter()
-                            src = f.read(1 << 20)
-                            st.read_s += time.perf_counter() - t0
-                            if not src:
-                                eof = True
-                                break
-                        t0 = time.perf_counter()
-                        out = dec.decompress(src, CHUNK_BYTES - n)
-                        st.inflate_s += time.perf_counter() - t0
-                        if out:
-                            mv[n:n + len(out)] = out
-                            n += len(out)
-                t0 = time.perf_counter()
-                check(self.lib.ac_sketch_feed(job, ptr, n, file_idx, 1 if eof else 0))
-                st.bytes_in += n
-                which ^= 1
-                fed_since_wait += 1
-                if fed_since_wait >= 2 and not eof:
-                    # both staging buffers are in flight: wait before overwriting the older one
-                    check(self.lib.ac_sketch_feed_wait(job))
-                    fed_since_wait = 0
-                st.feed_s += time.perf_counter() - t0
+        in_flight = 0
+
+        def feed(n: int, eof: int) -> None:
+            nonlocal which, in_flight
+            t0 = time.perf_counter()
+            check(self.lib.ac_sketch_feed(job, bufs[which][0], n, file_idx, eof))
+            st.bytes_in += n
+            which ^= 1
+            in_flight += 1
+            if in_flight >= 2 and not eof:
+                # both staging buffers are in flight: wait before overwriting the older one
+                check(self.lib.ac_sketch_feed_wait(job))
+                in_flight = 0
+            st.feed_s += time.perf_counter() - t0
+
+        fill = 0
+        for data in inflate.iter_inflated(path, st, self.inflate_threads):
+            mv = memoryview(data)
+            off = 0
+            while off < len(mv):
+                n = min(CHUNK_BYTES - fill, len(mv) - off)
+                bufs[which][1][fill:fill + n] = mv[off:off + n]
+                fill += n
+                off += n
+                if fill == CHUNK_BYTES:
+                    feed(fill, 0)
+                    fill = 0
+        feed(fill, 1)
         check(self.lib.ac_sketch_feed_wait(job))
 
     def _end(self, job: int, name: str, k: int, s: int, st: StreamStats) -> GpuSketch:
@@ -302,6 +277,8 @@ class MashGPU:
             raise
         sk = self._end(job, str(path), k, s, st)
         st.total_s = time.perf_counter() - t0
+        from . import fastx
+        fastx.record_size(path, sk.info["n_bases"])   # pyfastx `Fasta(path).size` for the FASTA genome-size QC
         return sk
 
     def sketch_bytes(self, bufs: Sequence[bytes], k: int = 27, s: int = 50000, m: int = 1, seed: int = 42,
@@ -372,6 +349,27 @@ class MashGPU:
                 o = qi * nr + ri
                 rows.append(DistRow(name, q.name, float(d[o]), float(p[o]), int(cm[o]), int(dn[o])))
         return rows
+
+
+    def load_sketch_set(self, sketches: Sequence[np.ndarray], lengths: Sequence[int], k: int, s: int,
+                        names: Optional[Sequence[str]] = None) -> GpuReferences:
+        """Upload many finished sketches (ascending hash arrays) as one device-resident set: the operand of
+        `dist_pairs` (all-vs-all `mash dist`, BASELINE config 5) or a reference set built in memory."""
+        from .msh import MshReference
+        refs = [MshReference(names[i] if names else f"sketch_{i}", "", int(lengths[i]),
+                             np.ascontiguousarray(h, np.uint64)) for i, h in enumerate(sketches)]
+        return self.load_references(MshSketch(kmer_size=k, sketch_size=s, hash_bits=64 if k > 16 else 32, references=refs))
+
+    def dist_pairs(self, a: GpuReferences, i0: int, ni: int, b: GpuReferences, j0: int, nj: int):
+        """One tile of `mash dist A B`: sketches a[i0:i0+ni] x b[j0:j0+nj] -> (distance, pvalue, common, denom),
+        each an [ni, nj] array."""
+        d = np.zeros((ni, nj), np.float64)
+        p = np.zeros((ni, nj), np.float64)
+        cm = np.zeros((ni, nj), np.uint64)
+        dn = np.zeros((ni, nj), np.uint64)
+        check(self.lib.ac_dist_pairs(self.ctx, a.handle, i0, ni, b.handle, j0, nj, d.ctypes.data, p.ctypes.data,
+                                     cm.ctypes.data, dn.ctypes.data))
+        return d, p, cm, dn
 
 
 def dist_stdout(rows: Iterable[DistRow]) -> str:

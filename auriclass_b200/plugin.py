@@ -18,6 +18,8 @@ from .workflow import MashGpuMethods, check_dependencies
 
 
 def install(device: int = 0) -> None:
+    from . import fastx
+    fastx.install_pyfastx_stub()   # the unchanged package imports pyfastx at module level (classes.py:9, general.py:7)
     classes = importlib.import_module("auriclass.classes")
     general = importlib.import_module("auriclass.general")
     MashGpuMethods.device = device
@@ -26,6 +28,7 @@ def install(device: int = 0) -> None:
     classes.BasicAuriclass.get_error_bounds = MashGpuMethods.get_error_bounds
     classes.FastqAuriclass.sketch_fastq_query = MashGpuMethods.sketch_fastq_query
     classes.FastaAuriclass.sketch_fasta_query = MashGpuMethods.sketch_fasta_query
+    classes.FastaAuriclass.parse_genome_size = MashGpuMethods.parse_genome_size
     general.check_dependencies = check_dependencies
     main = sys.modules.get("auriclass.main")
     if main is not None and hasattr(main, "check_dependencies"):

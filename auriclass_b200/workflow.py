@@ -166,6 +166,15 @@ class MashGpuMethods:
             for line in stderr.splitlines():
                 logging.info(add_tag("mash sketch", line))
 
+    # -- FastaAuriclass.parse_genome_size (classes.py:725-751): sum of pyfastx.Fasta(path).size over the inputs.
+    #    The GPU parser counted the bases while sketching, so this reads them back instead of re-indexing the file.
+    def parse_genome_size(self) -> None:
+        from . import fastx
+        total_size = 0
+        for filepath in self.read_paths:
+            total_size += fastx.Fasta(filepath, build_index=True).size
+        self.estimated_genome_size = total_size
+
     # -- mash dist REF Q   (classes.py:67-119)
     def run_mash_dist(self) -> pd.DataFrame:
         command = ["mash", "dist", self.reference_sketch_path, self.query_sketch_path]

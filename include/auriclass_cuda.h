@@ -75,6 +75,8 @@ typedef struct ac_sketch_info {
     double coverage;       /* sum_counts / n                      : `Estimated coverage`     */
     int32_t hash_bits;     /* 64 for k > 16 else 32                                          */
     int32_t passes;        /* hashing passes run (1 unless threshold speculation failed)     */
+    uint64_t n_bases;      /* sequence characters of ALL records (what pyfastx `Fasta(...).size`
+                              reports: auriclass/classes.py:746-751 sums it for the FASTA QC)   */
 } ac_sketch_info;
 
 /* ---- library / device ------------------------------------------------ */
@@ -157,6 +159,13 @@ int ac_dist(ac_ctx *ctx, const ac_refs *refs, const ac_sketch *query, double *di
 /* n_q queries against every reference: outputs are [n_q][n_refs] row-major. */
 int ac_dist_batch(ac_ctx *ctx, const ac_refs *refs, const ac_sketch *const *queries, int n_q,
                   double *distance, double *pvalue, uint64_t *common, uint64_t *denom);
+
+/* Tile of an all-vs-all `mash dist` (BASELINE config 5; `mash dist A.msh B.msh` with many sketches per file):
+ * sketches [i0, i0+ni) of set `a` against sketches [j0, j0+nj) of set `b` (the same handle for a self
+ * comparison).  Outputs are [ni][nj] row-major host arrays (any may be NULL).  Mash's row for a pair
+ * (reference = a[i], query = b[j]) carries exactly these four numbers. */
+int ac_dist_pairs(ac_ctx *ctx, const ac_refs *a, int i0, int ni, const ac_refs *b, int j0, int nj, double *distance,
+                  double *pvalue, uint64_t *common, uint64_t *denom);
 
 /* ---- instrumentation ------------------------------------------------- */
 /* Kernel launches issued by this context since creation (bench.py gpu_launches). */

@@ -3,6 +3,7 @@ the C-ABI surface, the .msh reader/writer, Mash text rendering and the bounds ta
 import ctypes as C
 import json
 import re
+import sys
 from io import StringIO
 from pathlib import Path
 
@@ -84,7 +85,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_sketch_info_struct_layout():
-    assert C.sizeof(_lib.SketchInfo) == 9 * 8 + 2 * 8 + 2 * 4
+    assert C.sizeof(_lib.SketchInfo) == 9 * 8 + 2 * 8 + 2 * 4 + 8
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -98,6 +99,29 @@ def test_no_cpu_fallback_without_gpu():
     from auriclass_b200.workflow import check_dependencies
     with pytest.raises(FileNotFoundError):
         check_dependencies()
+
+
+def test_plugin_grafts_onto_the_unchanged_reference_package():
+    """auriclass_b200.plugin.install() on the reference package itself (only where /root/reference is mounted):
+    the four subprocess methods, check_dependencies and parse_genome_size are re-pointed, and the package
+    imports although pyfastx is absent (stand-in module)."""
+    ref = Path("/root/reference")
+    if not (ref / "auriclass" / "classes.py").exists():
+        pytest.skip("reference package not mounted")
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import auriclass_b200.plugin as p; p.install()\n"
+        "import auriclass.classes as c, auriclass.general as g\n"
+        "from auriclass_b200.workflow import MashGpuMethods as M, check_dependencies as cd\n"
+        "assert c.BasicAuriclass.run_mash_dist is M.run_mash_dist and c.BasicAuriclass.get_error_bounds is M.get_error_bounds\n"
+        "assert c.FastqAuriclass.sketch_fastq_query is M.sketch_fastq_query and c.FastaAuriclass.sketch_fasta_query is M.sketch_fasta_query\n"
+        "assert c.FastaAuriclass.parse_genome_size is M.parse_genome_size and g.check_dependencies is cd\n"
+        "assert g.guess_input_type(['tests/data/NC_001416.1.fasta.gz']) == 'fasta'\n"
+        "assert g.guess_input_type(['tests/data/NC_001416.1_1.fq.gz', 'tests/data/NC_001416.1_2.fq.gz']) == 'fastq'\n"
+        "print('ok')\n") % (str(ref), str(ROOT))
+    import subprocess
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(ROOT))
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr[-2000:]
 
 
 def test_product_never_imports_oracle():
