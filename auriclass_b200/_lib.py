@@ -78,6 +78,7 @@ SIGNATURES = {
     "ac_set_profile": (C.c_int, [_vp, C.c_int]),
     "ac_last_job_times": (C.c_int, [_vp, C.POINTER(C.c_float * 4)]),
     "ac_int_peak": (C.c_int, [_vp, _dp]),
+    "ac_pipe_rates": (C.c_int, [_vp, C.POINTER(C.c_double * 3)]),
 }
 
 _lib = None

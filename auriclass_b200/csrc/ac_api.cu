@@ -359,6 +359,15 @@ extern "C" int ac_int_peak(ac_ctx *c, double *instr_per_s) {
     return AC_OK;
 }
 
+extern "C" int ac_pipe_rates(ac_ctx *c, double rates[3]) {
+    if (!c || !rates) return fail(AC_E_PARAM, "ac_pipe_rates: NULL argument");
+    CK(cudaSetDevice(c->dev));
+    LaunchCtx lc{c->s_comp, &c->launches};
+    run_pipe_rates(lc, rates);
+    CK(cudaGetLastError());
+    return AC_OK;
+}
+
 // ------------------------------------------------------------------ profiling helpers
 struct ProfScope {
     ac_ctx *c; int slot; cudaEvent_t a, b; bool on;
@@ -898,6 +907,9 @@ extern "C" int ac_sketch_end_local(ac_job *j, uint64_t *n_entries, uint64_t *tau
     CK(cudaSetDevice(c->dev));
     int rc = finish_local(j, true);
     if (rc) return rc;
+    CK(cudaEventRecord(c->ev_job1, c->s_comp));
+    CK(cudaStreamSynchronize(c->s_comp));
+    prof_collect(c);                      // ac_last_job_times covers the local pass of a sharded job
     const JobDev &h = *c->h_jd;
     j->ended_local = true;
     if (n_entries) *n_entries = h.n_table;

@@ -178,6 +178,7 @@ void launch_dist_pairs(const LaunchCtx &lc, const unsigned long long *a_hashes, 
                        unsigned long long *d_denom);
 
 double run_int_peak(const LaunchCtx &lc);
+void run_pipe_rates(const LaunchCtx &lc, double rates[3]);
 
 
 #if defined(__CUDACC__)

@@ -296,6 +296,31 @@ __global__ void __launch_bounds__(256) k_int_peak(uint32_t *out, int iters) {
     if (r == 0x12345678u) out[0] = r;  // never true in practice; keeps the chains alive
 }
 
+// ---- per-pipe issue rates: independent chains of ONE instruction kind (MODE 0: IMAD, 1: IMAD.WIDE.U32, 2: LOP3)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_pipe_rate(unsigned long long *out, int iters) {
+    uint32_t a[8];
+    unsigned long long w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a[i] = threadIdx.x + i; w[i] = (unsigned long long)threadIdx.x * 0x9E3779B97F4A7C15ULL + blockIdx.x + i; }
+    const uint32_t m = 0x9E3779B1u, c = 0x7F4A7C15u;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (MODE == 0) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(m), "r"(c));
+            else if (MODE == 1) {   // multiplicand = low word of the running value: nothing is loop invariant
+                const uint32_t lo = (uint32_t)w[i] ^ (uint32_t)(w[i] >> 32);   // both product halves stay live (one LOP3 on the other pipe)
+                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"(lo), "r"(m));
+            }
+            else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(m), "r"(c));
+        }
+    }
+    unsigned long long r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r ^= w[i] ^ a[i];
+    if ((uint32_t)r == 0x12345678u) out[0] = r;  // practically never true; keeps the chains alive
+}
+
 }  // namespace
 
 void launch_dist(const LaunchCtx &lc, const unsigned long long *ref_hashes, const unsigned long long *ref_off,
@@ -353,6 +378,41 @@ double run_int_peak(const LaunchCtx &lc) {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(d);
     return best;
+}
+
+template <int MODE>
+static double pipe_rate_one(const LaunchCtx &lc, unsigned long long *d, int sms) {
+    const int iters = 4096, blocks = sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0, lc.stream);
+        k_pipe_rate<MODE><<<blocks, threads, 0, lc.stream>>>(d, iters);
+        cudaEventRecord(e1, lc.stream);
+        cudaEventSynchronize(e1);
+        ++*lc.launches;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double instr = (double)blocks * threads * (double)iters * 8.0;
+        if (rep > 0 && ms > 0) best = fmax(best, instr / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return best;
+}
+
+// thread-instructions per second of IMAD, IMAD.WIDE.U32 and LOP3 issued alone (the pipes K2 lives on)
+void run_pipe_rates(const LaunchCtx &lc, double rates[3]) {
+    rates[0] = rates[1] = rates[2] = 0.0;
+    unsigned long long *d = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess) return;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    rates[0] = pipe_rate_one<0>(lc, d, sms);
+    rates[1] = pipe_rate_one<1>(lc, d, sms);
+    rates[2] = pipe_rate_one<2>(lc, d, sms);
+    cudaFree(d);
 }
 
 }  // namespace ac

@@ -189,6 +189,11 @@ class MashGPU:
         check(self.lib.ac_int_peak(self.ctx, C.byref(v)))
         return v.value
 
+    def pipe_rates(self) -> dict:
+        arr = (C.c_double * 3)()
+        check(self.lib.ac_pipe_rates(self.ctx, C.byref(arr)))
+        return {"imad": arr[0], "imad_wide": arr[1], "lop3": arr[2]}
+
     def _staging(self) -> List[Tuple[int, memoryview]]:
         if not self._pinned:
             for _ in range(2):

@@ -359,10 +359,13 @@ def main() -> None:
     sk = step_device()
     prof = eng.last_job_times()
     n_kmers, n_cand, passes = sk.info["n_kmers"], sk.info["n_candidates"], sk.info["passes"]
+    if world > 1:   # the sharded sketch reports job-wide counters; the rooflines are per GPU (equal shards)
+        n_kmers, n_cand = n_kmers // world, n_cand // world
     n_hashes = len(sk)
     sk.free()
     eng.set_profile(False)
     int_peak = eng.int_peak()
+    pipe = eng.pipe_rates()
 
     # max over ranks
     ms_step = float(np.mean(dev_ms)) if world == 1 else wall_ms
@@ -382,7 +385,13 @@ def main() -> None:
         n_rec = args.reads
         # K2 algorithmic bytes per step: the base stream (1 B per base + 1 separator per read) in, 8 B per candidate out
         k2_bytes = bases_per_rank + n_rec + 8 * n_cand
-        hash_s = prof["hash_ms"] * 1e-3
+        hash_s = max(prof["hash_ms"], 1e-6) * 1e-3
+        # pipe-cycle roofline of K2: per k-mer MurmurHash3_x64_128 over 27 bytes needs 14 IMAD.WIDE +
+        # 26 IMAD (12 64-bit multiplies by a constant = 1 wide + 2 low products each, two h*5+c) on the fmaheavy pipe and
+        # 44 SHF/LOP3/IADD3 on the alu pipe; the two pipes run concurrently, each at its own measured rate
+        fma_floor_s = n_kmers * (14.0 / pipe["imad_wide"] + 26.0 / pipe["imad"]) if min(pipe.values()) > 0 else 0.0
+        alu_floor_s = n_kmers * 44.0 / pipe["lop3"] if pipe["lop3"] > 0 else 0.0
+        floor_s = max(fma_floor_s, alu_floor_s)
         n_seg = -(-nbytes // (int(os.environ.get("AC_SEG_MB", "128")) << 20))  # K2 launches per step = segments (ac_common.cuh SEG_BYTES)
         traffic = None
         tp = ROOT / "profiles" / "k2_traffic.json"
@@ -423,6 +432,12 @@ def main() -> None:
             "roofline_int": {"bound": "int32-issue", "achieved": n_kmers * I_ALG / hash_s / 1e12, "peak": int_peak / 1e12,
                              "unit": "Tinstr/s", "frac": n_kmers * I_ALG / hash_s / int_peak,
                              "instr_per_kmer": I_ALG, "peak_source": "ac_int_peak: IMAD+LOP3 microbenchmark run in this process"},
+            "roofline_pipe": {"bound": "fmaheavy pipe (IMAD / IMAD.WIDE)" if fma_floor_s >= alu_floor_s else "alu pipe (SHF/LOP3/IADD3)",
+                              "floor_ms": floor_s * 1e3, "achieved_ms": hash_s * 1e3, "frac": floor_s / hash_s,
+                              "fma_floor_ms": fma_floor_s * 1e3, "alu_floor_ms": alu_floor_s * 1e3,
+                              "rates_Tinstr_per_s": {k: v / 1e12 for k, v in pipe.items()},
+                              "model": "per k-mer 14 IMAD.WIDE + 26 IMAD (fmaheavy) and 44 SHF/LOP3/IADD3 (alu), pipes concurrent; "
+                                       "rates measured in this process by ac_pipe_rates (one instruction kind issued alone)"},
             "kernel_ms": {"parse_k1": prof["parse_ms"], "hash_k2": prof["hash_ms"], "select_k3_k4": prof["select_ms"],
                           "job_total": prof["total_ms"]},
         }

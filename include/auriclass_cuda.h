@@ -180,6 +180,11 @@ int ac_last_job_times(const ac_ctx *ctx, float ms[4]);
  * int32 thread-instructions per second (the sketch roofline denominator). */
 int ac_int_peak(ac_ctx *ctx, double *instr_per_s);
 
+/* Issue rates (thread-instructions per second) of the three instruction kinds kernel K2 is made of, each
+ * issued alone in independent chains: [0] IMAD, [1] IMAD.WIDE.U32 (both on the fmaheavy pipe), [2] LOP3 (alu
+ * pipe).  bench.py turns them into the pipe-cycle roofline of the hash kernel. */
+int ac_pipe_rates(ac_ctx *ctx, double rates[3]);
+
 #ifdef __cplusplus
 }
 #endif
