@@ -229,6 +229,12 @@ def main() -> None:
         run_reference_arm(args)
         return
 
+    # the contract is ONE JSON line on stdout: libraries that write to fd 1 (NCCL prints its version banner there)
+    # are sent to stderr, the JSON line goes to a private duplicate of the original stdout
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -443,7 +449,7 @@ def main() -> None:
         }
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_sample(text, min(args.reads, args.cpu_sample_reads), rec)
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=json_out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
