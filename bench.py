@@ -359,6 +359,17 @@ def main() -> None:
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
     clocks = sampler.stop()
+    # the e2e path's own roofline: one plain H2D copy of the same pinned bytes (PCIe), CUDA events, best of 3
+    pinned_t = torch.from_numpy(text)
+    h2d_ms = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dev_text.copy_(pinned_t, non_blocking=True)
+        e1.record()
+        e1.synchronize()
+        h2d_ms.append(e0.elapsed_time(e1))
+    pcie_ms = min(h2d_ms)
 
     # ---- kernel breakdown of one more (profiled) step; integer peak
     eng.set_profile(True)
@@ -426,6 +437,7 @@ def main() -> None:
             "e2e": {"value": world * bases_per_rank / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s",
                     "ms_per_step": e2e_ms, "wall_s_per_isolate": e2e_ms * 1e-3,
                     "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(len(rows) * 32 + 8 * 256),
+                    "pcie_floor_ms": pcie_ms, "pcie_GBps": nbytes / pcie_ms / 1e6, "frac_of_pcie_floor": pcie_ms / e2e_ms,
                     "includes": "H2D of the FASTQ text from pinned memory in 32 MB feeds, sketch, dist vs "
                                 f"{len(rows)} references, D2H of the rows; gzip inflate not included (timed separately by the host streamer)"},
             "gpu_launches": int(launches),
