@@ -128,6 +128,8 @@ struct ac_job {
     size_t bytes_done, next_mark;
     uint32_t seg_serial, ticket_base; // segments / K1 tiles launched in the current pass
     bool ended_local;
+    bool table_pending;               // ended_local in count-table mode: the exchange table is cut straight from the count
+                                      // table, range by range, once tau_cut is known (ac_job_table_ranges)
 };
 
 struct ac_sketch {
@@ -416,7 +418,7 @@ extern "C" int ac_sketch_begin(ac_ctx *c, int k, int sketch_size, uint32_t seed,
     j->cur_file = -1; j->file_open = false; j->cur_fmt = -1; j->tail_len = 0;
     j->pass_started = false; j->tau0 = 0; j->safe = false; j->table = false; j->passes = 0;
     j->proc_piece = 0; j->proc_off = 0; j->pending = 0; j->first_of_stream = true;
-    j->cand_bound = 0; j->n_table_host = 0; j->tau_host = 0; j->bytes_done = 0; j->next_mark = 0; j->ended_local = false;
+    j->cand_bound = 0; j->n_table_host = 0; j->tau_host = 0; j->bytes_done = 0; j->next_mark = 0; j->ended_local = false; j->table_pending = false;
     for (auto &s : c->slabs) s.used = 0;
     c->cur_slab = 0;
     c->active = j;
@@ -486,6 +488,7 @@ static int start_pass(ac_job *j, unsigned long long tau0, bool safe) {
     CK(cudaStreamSynchronize(c->s_comp));
     if (j->passes == 0) CK(cudaEventRecord(c->ev_job0, c->s_comp));   // device time of a job starts before its table is cleared
     j->table = !safe && tau0 != space_max(j);
+    j->table_pending = false;
     if (j->table) {
         const size_t slots = (size_t)c->ct.mask + 1;
         CK(cudaMemsetAsync(c->ct.key, 0xff, slots * 8, c->s_comp));
@@ -786,19 +789,14 @@ static int finish_table(ac_job *j, bool for_exchange) {
     if (h.overflow) return AC_OK;                                   // table or list full: the caller repeats the pass by sorting
     if (h.n_qualified < (uint32_t)j->s) return AC_OK;               // speculation failed: the caller repeats it with tau = max
     const uint32_t n_q = h.n_qualified;
-    const int bits = key_bits_for(h.tau);
-    uint32_t n = n_q;
     if (for_exchange) {
-        launch_table_export(lc, c->ct, c->sb, c->d_jd);
-        CK(cudaGetLastError());
-        rc = read_jd(c);
-        if (rc) return rc;
-        n = c->h_jd->n_out;
-        if (n > c->sb.cap) return fail(AC_E_NOMEM, "exchange table needs %u entries, capacity %zu (raise AC_CAND_CAP)", n, c->sb.cap);
-    } else {
-        launch_table_collect(lc, c->ct, c->sb, c->d_jd, h.n_qlist);
+        // nothing to materialise yet: every rank's tau_r goes into the all-reduce first, then ac_job_table_ranges
+        // writes the entries <= tau_cut range by range straight from the count table (no sort on this side)
+        j->table_pending = true;
+        return AC_OK;
     }
-    launch_table_finish(lc, c->sb, c->d_jd, n, n_q, bits, j->s, for_exchange ? 1 : 0);
+    launch_table_collect(lc, c->ct, c->sb, c->d_jd, h.n_qlist);
+    launch_table_finish(lc, c->sb, c->d_jd, n_q, n_q, key_bits_for(h.tau), j->s, 0);
     CK(cudaGetLastError());
     return AC_OK;
 }
@@ -932,6 +930,26 @@ extern "C" int ac_job_table_ranges(ac_job *j, uint64_t tau_cut, int n_ranges, ui
     for (int r = 0; r < n_ranges; r++)
         rb.b[r] = (unsigned long long)((span * (unsigned)r + (unsigned)n_ranges - 1) / (unsigned)n_ranges);
     LaunchCtx lc{c->s_comp, &c->launches};
+    if (j->table_pending) {
+        // count-table mode: count the entries <= tau_cut per range, lay the ranges out back to back, fill them
+        if (tau_cut > c->h_jd->tau) return fail(AC_E_PARAM, "tau_cut above this rank's threshold: counts beyond it are not exact");
+        launch_table_range_count(lc, c->ct, rb, c->d_jd);
+        CK(cudaGetLastError());
+        int rc = read_jd(c);
+        if (rc) return rc;
+        RangeOffsets off;
+        memset(&off, 0, sizeof(off));
+        uint64_t run = 0;
+        for (int r = 0; r < n_ranges; r++) { off.o[r] = (uint32_t)run; range_begin[r] = run; run += c->h_jd->range_cnt[r]; }
+        off.o[n_ranges] = (uint32_t)run; range_begin[n_ranges] = run;
+        if (run > c->sb.tab_cap) return fail(AC_E_NOMEM, "exchange table needs %llu entries, capacity %zu (raise AC_CAND_CAP)", (unsigned long long)run, c->sb.tab_cap);
+        launch_table_range_scatter(lc, c->ct, rb, off, c->sb, c->d_jd);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(c->s_comp));
+        c->h_jd->n_table = (uint32_t)run;    // what ac_job_table_export checks its range against
+        j->table_pending = false;
+        return AC_OK;
+    }
     // the sort scratch is idle once the local pass has ended: its head receives the n_ranges+1 entry indices
     unsigned long long *d_out = c->sb.keys_b;
     launch_table_ranges(lc, c->sb, c->h_jd->n_table, rb, d_out);
@@ -944,6 +962,7 @@ extern "C" int ac_job_table_ranges(ac_job *j, uint64_t tau_cut, int n_ranges, ui
 extern "C" int ac_job_table_export(ac_job *j, uint64_t begin, uint64_t end, uint64_t *dev_hashes, uint32_t *dev_counts) {
     if (!j) return fail(AC_E_PARAM, "job is NULL");
     if (!j->ended_local) return fail(AC_E_STATE, "call ac_sketch_end_local first");
+    if (j->table_pending) return fail(AC_E_STATE, "call ac_job_table_ranges first: it lays the exchange table out");
     ac_ctx *c = j->ctx;
     CK(cudaSetDevice(c->dev));
     if (end < begin || end > c->h_jd->n_table) return fail(AC_E_PARAM, "table range [%llu,%llu) outside 0..%u",
@@ -965,9 +984,46 @@ extern "C" int ac_merge_counts(ac_ctx *c, uint64_t *dev_hashes, uint32_t *dev_co
     int rc = alloc_select(c, 1024);
     if (rc) return rc;
     if (n > c->sb.cap) return fail(AC_E_NOMEM, "merge of %llu entries exceeds capacity %zu", (unsigned long long)n, c->sb.cap);
+    if (c->active && !c->active->ended_local) return fail(AC_E_STATE, "ac_merge_counts while a sketch job is hashing on this context");
+    LaunchCtx lc{c->s_comp, &c->launches};
+    // through the count table when it can hold the entries at <= 25 % load: sums by atomicAdd, the keys whose sum
+    // reaches min_copies come back through the qualified list and only those (about s / P) are sorted
+    const size_t slots_full = (size_t)c->ct.mask + 1;
+    if (n * 4 <= slots_full && n < 0xffffffffull) {
+        size_t slots = 1u << 16;
+        while (slots < n * 4) slots <<= 1;
+        CountTable ct = c->ct;
+        ct.mask = (uint32_t)(slots - 1);
+        ct.min_copies = (uint32_t)min_copies;
+        ct.bshift = 0;
+        JobDev z;
+        memset(&z, 0, sizeof(z));
+        z.tau = ~0ULL;                       // k3t_collect keeps keys <= tau: all of them
+        *c->h_jd = z;
+        CK(cudaMemcpyAsync(c->d_jd, c->h_jd, sizeof(JobDev), cudaMemcpyHostToDevice, c->s_comp));
+        CK(cudaMemsetAsync(ct.key, 0xff, slots * 8, c->s_comp));
+        CK(cudaMemsetAsync(ct.cnt, 0, slots * 4, c->s_comp));
+        launch_merge_insert(lc, ct, (const unsigned long long *)dev_hashes, dev_counts, (uint32_t)n, c->d_jd);
+        CK(cudaGetLastError());
+        rc = read_jd(c);
+        if (rc) return rc;
+        if (!c->h_jd->overflow) {
+            const uint32_t nq = c->h_jd->n_qlist;
+            if (nq) {
+                launch_table_collect(lc, ct, c->sb, c->d_jd, nq);
+                launch_table_finish(lc, c->sb, c->d_jd, nq, nq, 64, 0x7fffffff, 1);   // sorted pairs -> (tab_hash, tab_cnt)
+                CK(cudaGetLastError());
+                CK(cudaMemcpyAsync(dev_hashes, c->sb.tab_hash, (size_t)nq * 8, cudaMemcpyDeviceToDevice, c->s_comp));
+                CK(cudaMemcpyAsync(dev_counts, c->sb.tab_cnt, (size_t)nq * 4, cudaMemcpyDeviceToDevice, c->s_comp));
+            }
+            CK(cudaStreamSynchronize(c->s_comp));
+            *n_out = nq;
+            return AC_OK;
+        }
+        // (a key equal to the table's "empty" marker, or a pathological probe sequence: sort instead)
+    }
     CK(cudaMemcpyAsync(c->sb.keys_a, dev_hashes, n * 8, cudaMemcpyDeviceToDevice, c->s_comp));
     CK(cudaMemcpyAsync(c->sb.vals_a, dev_counts, n * 4, cudaMemcpyDeviceToDevice, c->s_comp));
-    LaunchCtx lc{c->s_comp, &c->launches};
     launch_merge_counts(lc, c->sb, c->d_jd, n, min_copies);
     CK(cudaGetLastError());
     rc = read_jd(c);

@@ -24,6 +24,8 @@ constexpr int K2_W = 32;                             // window starts per hash t
 constexpr int K2_TILE = K2_THREADS * K2_W;           // window starts per hash CTA
 constexpr int K2_STAGE = K2_TILE / 8;                 // candidate staging slots per hash CTA (shared memory)
 
+constexpr int MAX_RANGES = 64;                       // hash ranges (= ranks) of the multi-GPU exchange
+
 enum { FMT_FASTQ = 0, FMT_FASTA = 1 };
 enum {  // JobDev::format_error bits
     FERR_FQ_HEADER = 1,   // a FASTQ record does not start with '@'
@@ -76,6 +78,7 @@ struct JobDev {
     unsigned long long total_vals;  // scratch
     uint32_t n_qlist;               // count-table mode: keys whose count reached min_copies so far (entries of the qualified list)
     uint32_t n_out;                 // count-table mode: entries written by the collect / export kernels
+    uint32_t range_cnt[MAX_RANGES];         // multi-GPU exchange: table entries <= tau_cut per hash range (MAX_RANGES), then write cursors
     // result (K4)
     unsigned long long max_hash, sum_counts;
     double genome_size, coverage;
@@ -155,7 +158,6 @@ void launch_table_export(const LaunchCtx &lc, const CountTable &ct, const Select
 void launch_table_finish(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, uint32_t n, uint32_t n_q, int key_bits,
                          int sketch_size, int all_entries);
 
-constexpr int MAX_RANGES = 64;  // hash ranges (= ranks) of the multi-GPU exchange
 struct RangeBounds {             // passed by value
     unsigned long long b[MAX_RANGES];  // b[r] = first hash owned by range r
     unsigned long long tau_cut;
@@ -163,6 +165,16 @@ struct RangeBounds {             // passed by value
 };
 void launch_table_ranges(const LaunchCtx &lc, const SelectBufs &sb, uint32_t n_table, const RangeBounds &bounds,
                          unsigned long long *d_out /*[n+1], device*/);
+// count-table mode, no sort: entries <= bounds.tau_cut counted per hash range into jd->range_cnt ...
+void launch_table_range_count(const LaunchCtx &lc, const CountTable &ct, const RangeBounds &bounds, JobDev *jd);
+// ... and, with the ranges' exclusive offsets, written range by range (any order inside a range) to (tab_hash, tab_cnt)
+struct RangeOffsets { uint32_t o[MAX_RANGES + 1]; };
+void launch_table_range_scatter(const LaunchCtx &lc, const CountTable &ct, const RangeBounds &bounds, const RangeOffsets &off,
+                                const SelectBufs &sb, JobDev *jd);
+// owner merge through the count table: (hash, count) DEVICE pairs in any order are added up; every hash whose sum
+// reaches min_copies lands in ct.qlist (jd->n_qlist); jd->overflow when the table cannot hold them
+void launch_merge_insert(const LaunchCtx &lc, const CountTable &ct, const unsigned long long *hashes, const uint32_t *counts,
+                         uint32_t n, JobDev *jd);
 
 void launch_dist(const LaunchCtx &lc, const unsigned long long *ref_hashes, const unsigned long long *ref_off,
                  const unsigned long long *ref_len, int n_refs, const unsigned long long *const *q_hashes,

@@ -14,6 +14,8 @@
 //   table is truncated there.
 // Entries above the s-th qualified hash can never enter the sketch (App. A.4), so
 // tau only ever shrinks and counts of everything <= tau stay exact.
+#include <stddef.h>
+
 #include "ac_common.cuh"
 
 namespace ac {
@@ -410,6 +412,84 @@ __global__ void __launch_bounds__(256) k3t_finish(const u64 *__restrict__ keys, 
     if (i == 0) { jd->n_table = n; jd->n_unique = n; jd->n_qualified = n_q; jd->n_sketch = n_sketch; jd->cand_count = 0; }
 }
 
+// ---- multi-GPU exchange straight from the count table (no sort): owner of hash x = #{r >= 1 : b[r] <= x}
+__device__ __forceinline__ int range_of(const RangeBounds &rb, u64 x) {
+    int r = 0;
+    for (int j = 1; j < rb.n; j++) r += (x >= rb.b[j]) ? 1 : 0;
+    return r;
+}
+
+constexpr int RG_THREADS = 256;
+constexpr int RG_CTAS = 148 * 4;
+
+__global__ void __launch_bounds__(RG_THREADS) k3t_range_count(const CountTable ct, const RangeBounds rb, JobDev *__restrict__ jd) {
+    __shared__ uint32_t s_cnt[MAX_RANGES];
+    if (threadIdx.x < MAX_RANGES) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u64 slots = (u64)ct.mask + 1, per = (slots + gridDim.x - 1) / gridDim.x;
+    const u64 lo = (u64)blockIdx.x * per, hi = lo + per < slots ? lo + per : slots;
+    for (u64 slot = lo + threadIdx.x; slot < hi; slot += RG_THREADS) {
+        const u64 h = __ldcg(ct.key + slot);
+        if (h != CT_EMPTY && h <= rb.tau_cut) atomicAdd(&s_cnt[range_of(rb, h)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < rb.n && s_cnt[threadIdx.x]) atomicAdd(&jd->range_cnt[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+// the same walk; a CTA reserves its share of every range with one atomic per range, then fills it
+__global__ void __launch_bounds__(RG_THREADS) k3t_range_scatter(const CountTable ct, const RangeBounds rb, const RangeOffsets off,
+                                                                JobDev *__restrict__ jd, u64 *__restrict__ out_hash,
+                                                                uint32_t *__restrict__ out_cnt) {
+    __shared__ uint32_t s_cnt[MAX_RANGES], s_base[MAX_RANGES];
+    if (threadIdx.x < MAX_RANGES) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u64 slots = (u64)ct.mask + 1, per = (slots + gridDim.x - 1) / gridDim.x;
+    const u64 lo = (u64)blockIdx.x * per, hi = lo + per < slots ? lo + per : slots;
+    for (u64 slot = lo + threadIdx.x; slot < hi; slot += RG_THREADS) {
+        const u64 h = __ldcg(ct.key + slot);
+        if (h != CT_EMPTY && h <= rb.tau_cut) atomicAdd(&s_cnt[range_of(rb, h)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < rb.n) {
+        const uint32_t c = s_cnt[threadIdx.x];
+        s_base[threadIdx.x] = off.o[threadIdx.x] + (c ? atomicAdd(&jd->range_cnt[threadIdx.x], c) : 0u);
+        s_cnt[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    for (u64 slot = lo + threadIdx.x; slot < hi; slot += RG_THREADS) {
+        const u64 h = __ldcg(ct.key + slot);
+        if (h != CT_EMPTY && h <= rb.tau_cut) {
+            const int r = range_of(rb, h);
+            const uint32_t pos = s_base[r] + atomicAdd(&s_cnt[r], 1u);
+            out_hash[pos] = h; out_cnt[pos] = __ldcg(ct.cnt + slot);
+        }
+    }
+}
+
+// owner merge: add (hash, count) pairs into the table; the addition that carries a sum across min_copies qualifies the key
+__global__ void __launch_bounds__(256) k3t_merge_insert(const CountTable ct, const u64 *__restrict__ hashes,
+                                                        const uint32_t *__restrict__ counts, uint32_t n, JobDev *__restrict__ jd) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 h = hashes[i];
+    const uint32_t c = counts[i];
+    if (h == CT_EMPTY) { jd->overflow = 1u; return; }     // the one value the table cannot key: the caller sorts instead
+    uint32_t slot = (uint32_t)h & ct.mask;
+    for (int probe = 0; probe < CT_MAX_PROBE; probe++, slot = (slot + 1u) & ct.mask) {
+        u64 cur = __ldcg(ct.key + slot);
+        if (cur == CT_EMPTY) cur = atomicCAS(ct.key + slot, CT_EMPTY, h);
+        if (cur == CT_EMPTY || cur == h) {
+            const uint32_t old = atomicAdd(ct.cnt + slot, c);
+            if (old < ct.min_copies && old + c >= ct.min_copies) {
+                const uint32_t q = atomicAdd(&jd->n_qlist, 1u);
+                if (q < ct.qcap) ct.qlist[q] = h; else jd->overflow = 1u;
+            }
+            return;
+        }
+    }
+    jd->overflow = 1u;
+}
+
 void runs_and_qualify(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, const u64 *keys, const uint32_t *vals,
                       uint32_t n, int sketch_size, int min_copies, u64 *out_hash, uint32_t *out_cnt, int compact) {
     const uint32_t n_tiles = div_up(n ? n : 1, SC_TILE);
@@ -465,6 +545,26 @@ void launch_table_finish(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, 
     // all_entries: the pairs include unqualified keys (exchange table), so there is no sketch prefix to copy
     k3t_finish<<<div_up(n ? n : 1, 256), 256, 0, lc.stream>>>(keys, vals, n, all_entries ? 0u : n_sk, n_q, n_sk, sb.tab_hash,
                                                               sb.tab_cnt, sb.sk_hash, sb.sk_cnt, jd);
+    ++*lc.launches;
+}
+
+void launch_table_range_count(const LaunchCtx &lc, const CountTable &ct, const RangeBounds &bounds, JobDev *jd) {
+    cudaMemsetAsync((char *)jd + offsetof(JobDev, range_cnt), 0, sizeof(uint32_t) * MAX_RANGES, lc.stream);
+    k3t_range_count<<<RG_CTAS, RG_THREADS, 0, lc.stream>>>(ct, bounds, jd);
+    ++*lc.launches;
+}
+
+void launch_table_range_scatter(const LaunchCtx &lc, const CountTable &ct, const RangeBounds &bounds, const RangeOffsets &off,
+                                const SelectBufs &sb, JobDev *jd) {
+    cudaMemsetAsync((char *)jd + offsetof(JobDev, range_cnt), 0, sizeof(uint32_t) * MAX_RANGES, lc.stream);   // now the per-range write cursors
+    k3t_range_scatter<<<RG_CTAS, RG_THREADS, 0, lc.stream>>>(ct, bounds, off, jd, sb.tab_hash, sb.tab_cnt);
+    ++*lc.launches;
+}
+
+void launch_merge_insert(const LaunchCtx &lc, const CountTable &ct, const unsigned long long *hashes, const uint32_t *counts,
+                         uint32_t n, JobDev *jd) {
+    if (!n) return;
+    k3t_merge_insert<<<div_up(n, 256), 256, 0, lc.stream>>>(ct, hashes, counts, n, jd);
     ++*lc.launches;
 }
 

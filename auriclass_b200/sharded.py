@@ -125,6 +125,7 @@ class ShardedSketcher:
         self.backend = backend if backend is not None else CudaTableBackend(engine)
         self.device = self.backend.device
         self.last_exchange = {}
+        self._mark = None   # optional callable(name): phase timing hook (tools/time_sharded.py)
 
     # -- step 1
     def _tau_cut(self, tau_local: int) -> int:
@@ -135,7 +136,9 @@ class ShardedSketcher:
     def finish(self, job, k: int, s: int, m: int, name: str = "reads"):
         """Collective: every rank calls it with its own job; every rank returns the same sketch."""
         P = self.world
+        mark = self._mark or (lambda name: None)
         splits, tab = self.backend.local_table(job, self._tau_cut, P)
+        mark("local_table")
         # -- step 2: sizes, then payload
         send_n = torch.tensor(splits, dtype=torch.int64, device=self.device)
         recv_n = torch.empty(P, dtype=torch.int64, device=self.device)
@@ -146,9 +149,11 @@ class ShardedSketcher:
         rc = torch.empty(max(n_recv, 1), dtype=torch.int32, device=self.device)[:n_recv]
         dist.all_to_all_single(rh, tab.hashes, rsplits, splits, group=self.group)
         dist.all_to_all_single(rc, tab.counts, rsplits, splits, group=self.group)
+        mark("all_to_all")
         # -- step 3: owner merge (exact counts of this rank's hash range)
         n_q = self.backend.merge_counts(rh, rc, m)
         n_keep = min(n_q, s)
+        mark("merge_counts")
         # -- step 4: gather the owners' prefixes and the job counters
         meta = torch.tensor([n_keep, n_q, *tab.counters], dtype=torch.int64, device=self.device)
         metas = torch.empty(P * meta.numel(), dtype=torch.int64, device=self.device)
@@ -164,6 +169,7 @@ class ShardedSketcher:
         gc = torch.empty(P * pad, dtype=torch.int32, device=self.device)
         dist.all_gather_into_tensor(gh, sh, group=self.group)
         dist.all_gather_into_tensor(gc, sc, group=self.group)
+        mark("all_gather")
         # ordered concatenation (range r < range r+1), first s entries
         parts_h, parts_c, left = [], [], s
         for r in range(P):
