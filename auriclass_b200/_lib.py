@@ -50,6 +50,7 @@ SIGNATURES = {
     "ac_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "ac_destroy": (None, [_vp]),
     "ac_sync": (C.c_int, [_vp]),
+    "ac_set_stream": (C.c_int, [_vp, _vp, C.c_int]),
     "ac_alloc_pinned": (_vp, [C.c_size_t]),
     "ac_free_pinned": (None, [_vp]),
     "ac_sketch_begin": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int, C.POINTER(_vp)]),

@@ -71,6 +71,8 @@ struct SketchBuf { unsigned long long *h; uint32_t *c; uint64_t cap; };
 struct ac_ctx {
     int dev;
     cudaStream_t s_copy, s_comp;
+    cudaStream_t s_own;        // the compute stream this context created (s_comp unless the caller injected one)
+    bool stream_injected;      // s_comp belongs to the caller (ac_set_stream): device-side outputs are stream ordered, not synced
     uint64_t launches;
     float last_ms[4];
     bool profile;
@@ -293,6 +295,7 @@ extern "C" int ac_create(int device, ac_ctx **out) {
     if (c->seg_bytes > ((size_t)1 << 30)) c->seg_bytes = (size_t)1 << 30;
     CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+    c->s_own = c->s_comp; c->stream_injected = false;
     for (int i = 0; i < 2; i++) CK(cudaMalloc(&c->d_Z[i], Z_CARRY + c->seg_bytes + K1_TILE + K2_TILE + 4096));
     c->max_tiles = c->seg_bytes / K1_TILE + 4;
     CK(cudaMalloc(&c->d_st1, c->max_tiles * 8)); CK(cudaMalloc(&c->d_st2, c->max_tiles * 8));
@@ -326,7 +329,7 @@ extern "C" void ac_destroy(ac_ctx *c) {
     for (auto ev : c->ev_pool) cudaEventDestroy(ev);
     for (int i = 0; i < 3; i++) for (auto &p : c->prof[i]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     cudaEventDestroy(c->ev_job0); cudaEventDestroy(c->ev_job1);
-    cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_comp);
+    cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_own);
     delete c;
 }
 
@@ -335,6 +338,16 @@ extern "C" int ac_sync(ac_ctx *c) {
     CK(cudaSetDevice(c->dev));
     CK(cudaStreamSynchronize(c->s_copy));
     CK(cudaStreamSynchronize(c->s_comp));
+    return AC_OK;
+}
+
+extern "C" int ac_set_stream(ac_ctx *c, void *stream, int injected) {
+    if (!c) return fail(AC_E_PARAM, "ac_set_stream: ctx is NULL");
+    if (c->active) return fail(AC_E_STATE, "ac_set_stream while a sketch job is active");
+    CK(cudaSetDevice(c->dev));
+    CK(cudaStreamSynchronize(c->s_comp));
+    if (injected) { c->s_comp = (cudaStream_t)stream; c->stream_injected = true; }
+    else { c->s_comp = c->s_own; c->stream_injected = false; }
     return AC_OK;
 }
 
@@ -816,8 +829,10 @@ static int finish_local(ac_job *j, bool for_exchange = false) {
         }
         rc = j->table ? finish_table(j, for_exchange) : consolidate(j);
         if (rc) return rc;
-        rc = read_jd(c);
-        if (rc) return rc;
+        if (!j->table_pending) {       // (a pending exchange table: finish_table's read is still current, nothing ran since)
+            rc = read_jd(c);
+            if (rc) return rc;
+        }
         tr.mark("  table/consolidate");
         const JobDev &h = *c->h_jd;
         uint32_t ferr = h.format_error;
@@ -903,8 +918,10 @@ extern "C" int ac_sketch_end_local(ac_job *j, uint64_t *n_entries, uint64_t *tau
     if (!j) return fail(AC_E_PARAM, "job is NULL");
     ac_ctx *c = j->ctx;
     CK(cudaSetDevice(c->dev));
+    Trace tr;
     int rc = finish_local(j, true);
     if (rc) return rc;
+    tr.mark("end_local: finish_local");
     CK(cudaEventRecord(c->ev_job1, c->s_comp));
     CK(cudaStreamSynchronize(c->s_comp));
     prof_collect(c);                      // ac_last_job_times covers the local pass of a sharded job
@@ -931,12 +948,14 @@ extern "C" int ac_job_table_ranges(ac_job *j, uint64_t tau_cut, int n_ranges, ui
         rb.b[r] = (unsigned long long)((span * (unsigned)r + (unsigned)n_ranges - 1) / (unsigned)n_ranges);
     LaunchCtx lc{c->s_comp, &c->launches};
     if (j->table_pending) {
+        Trace tr;
         // count-table mode: count the entries <= tau_cut per range, lay the ranges out back to back, fill them
         if (tau_cut > c->h_jd->tau) return fail(AC_E_PARAM, "tau_cut above this rank's threshold: counts beyond it are not exact");
         launch_table_range_count(lc, c->ct, rb, c->d_jd);
         CK(cudaGetLastError());
         int rc = read_jd(c);
         if (rc) return rc;
+        tr.mark("ranges: count+read");
         RangeOffsets off;
         memset(&off, 0, sizeof(off));
         uint64_t run = 0;
@@ -945,9 +964,10 @@ extern "C" int ac_job_table_ranges(ac_job *j, uint64_t tau_cut, int n_ranges, ui
         if (run > c->sb.tab_cap) return fail(AC_E_NOMEM, "exchange table needs %llu entries, capacity %zu (raise AC_CAND_CAP)", (unsigned long long)run, c->sb.tab_cap);
         launch_table_range_scatter(lc, c->ct, rb, off, c->sb, c->d_jd);
         CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(c->s_comp));
+        if (!c->stream_injected) CK(cudaStreamSynchronize(c->s_comp));
         c->h_jd->n_table = (uint32_t)run;    // what ac_job_table_export checks its range against
         j->table_pending = false;
+        tr.mark("ranges: scatter launch");
         return AC_OK;
     }
     // the sort scratch is idle once the local pass has ended: its head receives the n_ranges+1 entry indices
@@ -972,7 +992,7 @@ extern "C" int ac_job_table_export(ac_job *j, uint64_t begin, uint64_t end, uint
         CK(cudaMemcpyAsync(dev_hashes, c->sb.tab_hash + begin, n * 8, cudaMemcpyDeviceToDevice, c->s_comp));
         CK(cudaMemcpyAsync(dev_counts, c->sb.tab_cnt + begin, n * 4, cudaMemcpyDeviceToDevice, c->s_comp));
     }
-    CK(cudaStreamSynchronize(c->s_comp));
+    if (!c->stream_injected) CK(cudaStreamSynchronize(c->s_comp));
     return AC_OK;
 }
 
@@ -1011,12 +1031,12 @@ extern "C" int ac_merge_counts(ac_ctx *c, uint64_t *dev_hashes, uint32_t *dev_co
             const uint32_t nq = c->h_jd->n_qlist;
             if (nq) {
                 launch_table_collect(lc, ct, c->sb, c->d_jd, nq);
-                launch_table_finish(lc, c->sb, c->d_jd, nq, nq, 64, 0x7fffffff, 1);   // sorted pairs -> (tab_hash, tab_cnt)
+                launch_table_finish(lc, c->sb, c->d_jd, nq, nq, key_bits_for(c->h_jd->max_hash), 0x7fffffff, 1);   // sorted pairs -> (tab_hash, tab_cnt)
                 CK(cudaGetLastError());
                 CK(cudaMemcpyAsync(dev_hashes, c->sb.tab_hash, (size_t)nq * 8, cudaMemcpyDeviceToDevice, c->s_comp));
                 CK(cudaMemcpyAsync(dev_counts, c->sb.tab_cnt, (size_t)nq * 4, cudaMemcpyDeviceToDevice, c->s_comp));
             }
-            CK(cudaStreamSynchronize(c->s_comp));
+            if (!c->stream_injected) CK(cudaStreamSynchronize(c->s_comp));
             *n_out = nq;
             return AC_OK;
         }

@@ -137,6 +137,97 @@ int radix_sort_pairs(const LaunchCtx &lc, u64 *ka, uint32_t *va, u64 *kb, uint32
     return cur;
 }
 
+// ------------------------------------------------------- small sort of hash values (bucket sort)
+// The <= ~s pairs a count-table pass ends with are MurmurHash3 values spread evenly over [0, tau]: bucketing by
+// the top 16 bits below tau's top bit leaves about one key per bucket, so hist -> scan -> scatter -> a per-bucket
+// fix-up orders them in 4 launches where the 8-bit LSD radix sort needs 24.  Exact for any input (a crowded
+// bucket is only slow: its fix-up is one thread's heap sort).
+constexpr int BS_BITS = 16;
+constexpr int BS_BUCKETS = 1 << BS_BITS;
+
+__global__ void __launch_bounds__(256) bs_hist(const u64 *__restrict__ keys, uint32_t n, int shift, uint32_t *__restrict__ hist) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(hist + (uint32_t)(keys[i] >> shift), 1u);
+}
+
+// one CTA: exclusive scan of the bucket counts -> start[], cursors zeroed
+__global__ void __launch_bounds__(1024) bs_scan(const uint32_t *__restrict__ hist, uint32_t *__restrict__ start,
+                                                uint32_t *__restrict__ cursor) {
+    __shared__ uint32_t s_w[33];
+    constexpr int PER = BS_BUCKETS / 1024;
+    const uint32_t t = threadIdx.x;
+    uint32_t v[PER], mine = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) { v[i] = hist[t * PER + i]; mine += v[i]; }
+    uint32_t total;
+    uint32_t run = block_excl_sum<1024>(mine, s_w, total);
+#pragma unroll
+    for (int i = 0; i < PER; i++) { start[t * PER + i] = run; cursor[t * PER + i] = 0; run += v[i]; }
+    if (t == 1023) start[BS_BUCKETS] = run;
+}
+
+__global__ void __launch_bounds__(256) bs_scatter(const u64 *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n,
+                                                  int shift, const uint32_t *__restrict__ start, uint32_t *__restrict__ cursor,
+                                                  u64 *__restrict__ okeys, uint32_t *__restrict__ ovals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 k = keys[i];
+    const uint32_t b = (uint32_t)(k >> shift);
+    const uint32_t pos = start[b] + atomicAdd(cursor + b, 1u);
+    okeys[pos] = k; ovals[pos] = vals[i];
+}
+
+__device__ void bs_sift_down(u64 *k, uint32_t *v, uint32_t root, uint32_t end) {
+    for (;;) {
+        uint32_t child = 2 * root + 1;
+        if (child >= end) return;
+        if (child + 1 < end && k[child] < k[child + 1]) child++;
+        if (k[root] >= k[child]) return;
+        const u64 tk = k[root]; k[root] = k[child]; k[child] = tk;
+        const uint32_t tv = v[root]; v[root] = v[child]; v[child] = tv;
+        root = child;
+    }
+}
+
+// one thread per bucket: order its (few) entries
+__global__ void __launch_bounds__(256) bs_fix(const uint32_t *__restrict__ start, u64 *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= BS_BUCKETS) return;
+    const uint32_t lo = start[b], n = start[b + 1] - lo;
+    if (n < 2) return;
+    u64 *k = keys + lo;
+    uint32_t *v = vals + lo;
+    if (n <= 32) {
+        for (uint32_t i = 1; i < n; i++) {
+            const u64 kk = k[i];
+            const uint32_t vv = v[i];
+            uint32_t jx = i;
+            while (jx > 0 && k[jx - 1] > kk) { k[jx] = k[jx - 1]; v[jx] = v[jx - 1]; jx--; }
+            k[jx] = kk; v[jx] = vv;
+        }
+        return;
+    }
+    for (uint32_t i = n / 2; i-- > 0;) bs_sift_down(k, v, i, n);          // crowded bucket: in-place heap sort
+    for (uint32_t end = n - 1; end > 0; end--) {
+        const u64 tk = k[0]; k[0] = k[end]; k[end] = tk;
+        const uint32_t tv = v[0]; v[0] = v[end]; v[end] = tv;
+        bs_sift_down(k, v, 0, end);
+    }
+}
+
+// sorts n pairs (keys <= 2^key_bits - 1) from (ka, va) into (kb, vb); hist scratch: 3 * BS_BUCKETS + 1 words
+void bucket_sort_pairs(const LaunchCtx &lc, const u64 *ka, const uint32_t *va, u64 *kb, uint32_t *vb, uint32_t n, int key_bits,
+                       uint32_t *scratch) {
+    const int shift = key_bits > BS_BITS ? key_bits - BS_BITS : 0;
+    uint32_t *hist = scratch, *start = scratch + BS_BUCKETS, *cursor = scratch + 2 * BS_BUCKETS + 1;
+    cudaMemsetAsync(hist, 0, BS_BUCKETS * sizeof(uint32_t), lc.stream);
+    bs_hist<<<div_up(n, 256), 256, 0, lc.stream>>>(ka, n, shift, hist);
+    bs_scan<<<1, 1024, 0, lc.stream>>>(hist, start, cursor);
+    bs_scatter<<<div_up(n, 256), 256, 0, lc.stream>>>(ka, va, n, shift, start, cursor, kb, vb);
+    bs_fix<<<BS_BUCKETS / 256, 256, 0, lc.stream>>>(start, kb, vb);
+    *lc.launches += 4;
+}
+
 // ------------------------------------------------------- consolidation
 // vals of the fresh candidates are an implicit 1; table entries are appended behind them
 __global__ void k3_prepare(u64 *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t n_cand,
@@ -481,6 +572,7 @@ __global__ void __launch_bounds__(256) k3t_merge_insert(const CountTable ct, con
         if (cur == CT_EMPTY || cur == h) {
             const uint32_t old = atomicAdd(ct.cnt + slot, c);
             if (old < ct.min_copies && old + c >= ct.min_copies) {
+                atomicMax(&jd->max_hash, h);               // the sort of the qualified keys sizes its buckets with it
                 const uint32_t q = atomicAdd(&jd->n_qlist, 1u);
                 if (q < ct.qcap) ct.qlist[q] = h; else jd->overflow = 1u;
             }
@@ -537,34 +629,22 @@ void launch_table_export(const LaunchCtx &lc, const CountTable &ct, const Select
 
 void launch_table_finish(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, uint32_t n, uint32_t n_q, int key_bits,
                          int sketch_size, int all_entries) {
-    const int where = radix_sort_pairs(lc, sb.keys_a, sb.vals_a, sb.keys_b, sb.vals_b, n, key_bits, sb.hist,
-                                       sb.hist + (size_t)256 * div_up(n ? n : 1, RS_TILE));
-    const u64 *keys = where ? sb.keys_b : sb.keys_a;
-    const uint32_t *vals = where ? sb.vals_b : sb.vals_a;
+    const u64 *keys;
+    const uint32_t *vals;
+    if (n >= 2 && n <= (1u << 20) && (size_t)256 * div_up(sb.cap, RS_TILE) >= (size_t)3 * BS_BUCKETS + 2) {
+        // few, evenly spread hash values: bucket sort (4 launches) into the idle ping-pong pair
+        bucket_sort_pairs(lc, sb.keys_a, sb.vals_a, sb.keys_b, sb.vals_b, n, key_bits, sb.hist);
+        keys = sb.keys_b; vals = sb.vals_b;
+    } else {
+        const int where = radix_sort_pairs(lc, sb.keys_a, sb.vals_a, sb.keys_b, sb.vals_b, n, key_bits, sb.hist,
+                                           sb.hist + (size_t)256 * div_up(n ? n : 1, RS_TILE));
+        keys = where ? sb.keys_b : sb.keys_a;
+        vals = where ? sb.vals_b : sb.vals_a;
+    }
     const uint32_t n_sk = n_q < (uint32_t)sketch_size ? n_q : (uint32_t)sketch_size;
     // all_entries: the pairs include unqualified keys (exchange table), so there is no sketch prefix to copy
     k3t_finish<<<div_up(n ? n : 1, 256), 256, 0, lc.stream>>>(keys, vals, n, all_entries ? 0u : n_sk, n_q, n_sk, sb.tab_hash,
                                                               sb.tab_cnt, sb.sk_hash, sb.sk_cnt, jd);
-    ++*lc.launches;
-}
-
-void launch_table_range_count(const LaunchCtx &lc, const CountTable &ct, const RangeBounds &bounds, JobDev *jd) {
-    cudaMemsetAsync((char *)jd + offsetof(JobDev, range_cnt), 0, sizeof(uint32_t) * MAX_RANGES, lc.stream);
-    k3t_range_count<<<RG_CTAS, RG_THREADS, 0, lc.stream>>>(ct, bounds, jd);
-    ++*lc.launches;
-}
-
-void launch_table_range_scatter(const LaunchCtx &lc, const CountTable &ct, const RangeBounds &bounds, const RangeOffsets &off,
-                                const SelectBufs &sb, JobDev *jd) {
-    cudaMemsetAsync((char *)jd + offsetof(JobDev, range_cnt), 0, sizeof(uint32_t) * MAX_RANGES, lc.stream);   // now the per-range write cursors
-    k3t_range_scatter<<<RG_CTAS, RG_THREADS, 0, lc.stream>>>(ct, bounds, off, jd, sb.tab_hash, sb.tab_cnt);
-    ++*lc.launches;
-}
-
-void launch_merge_insert(const LaunchCtx &lc, const CountTable &ct, const unsigned long long *hashes, const uint32_t *counts,
-                         uint32_t n, JobDev *jd) {
-    if (!n) return;
-    k3t_merge_insert<<<div_up(n, 256), 256, 0, lc.stream>>>(ct, hashes, counts, n, jd);
     ++*lc.launches;
 }
 

@@ -74,6 +74,18 @@ class CudaTableBackend:
         self.eng = engine
         self.lib = engine.lib
         self.device = torch.device("cuda", engine.device)
+        self.stream_shared = False
+
+    def share_torch_stream(self) -> None:
+        """Run the library's kernels on torch's current stream: the collectives torch.distributed queues on that
+        stream are then ordered against them on the device and no host synchronisation is needed in between."""
+        check(self.lib.ac_set_stream(self.eng.ctx, torch.cuda.current_stream(self.device).cuda_stream, 1))
+        self.stream_shared = True
+
+    def unshare_stream(self) -> None:
+        if self.stream_shared:
+            check(self.lib.ac_set_stream(self.eng.ctx, None, 0))
+            self.stream_shared = False
 
     def local_table(self, job: int, tau_cut_fn, n_ranges: int):
         """End the local pass; returns (send splits, LocalTable restricted to <= tau_cut)."""
@@ -81,18 +93,34 @@ class CudaTableBackend:
         tau = C.c_uint64()
         spec = C.c_int()
         info = SketchInfo()
+        import time as _t
+        _t0 = _t.perf_counter()
+        _tr = []
         try:
             check(self.lib.ac_sketch_end_local(job, C.byref(n), C.byref(tau), C.byref(spec), C.byref(info)))
+            _tr.append(("end_local", _t.perf_counter()))
             tau_cut = tau_cut_fn(int(tau.value))
+            _tr.append(("tau_cut", _t.perf_counter()))
             begins = (C.c_uint64 * (n_ranges + 1))()
             check(self.lib.ac_job_table_ranges(job, tau_cut, n_ranges, begins))
+            _tr.append(("ranges", _t.perf_counter()))
             b = [int(x) for x in begins]
             n_send = b[n_ranges]
             h = torch.empty(max(n_send, 1), dtype=torch.int64, device=self.device)
             c = torch.empty(max(n_send, 1), dtype=torch.int32, device=self.device)
             check(self.lib.ac_job_table_export(job, 0, n_send, h.data_ptr(), c.data_ptr()))
+            _tr.append(("export", _t.perf_counter()))
         finally:
             self.lib.ac_sketch_abort(job)  # frees the job; the exported copy is ours
+        _tr.append(("abort", _t.perf_counter()))
+        import os as _os
+        if _os.environ.get("AC_TRACE"):
+            prev = _t0
+            out = []
+            for nm, tt in _tr:
+                out.append(f"{nm} {1e3 * (tt - prev):.3f}")
+                prev = tt
+            print("[py trace] " + " | ".join(out), flush=True)
         splits = [b[r + 1] - b[r] for r in range(n_ranges)]
         counters = (info.n_records, info.n_kept, info.total_len, info.n_kmers, info.n_candidates)
         return splits, LocalTable(h[:n_send], c[:n_send], tau_cut, counters)
@@ -103,7 +131,8 @@ class CudaTableBackend:
         n = hashes.numel()
         if n == 0:
             return 0
-        torch.cuda.current_stream(self.device).synchronize()  # NCCL wrote these on torch's stream; the library has its own
+        if not self.stream_shared:
+            torch.cuda.current_stream(self.device).synchronize()  # NCCL wrote these on torch's stream; the library has its own
         check(self.lib.ac_merge_counts(self.eng.ctx, hashes.data_ptr(), counts.data_ptr(), n, min_copies, C.byref(n_out)))
         return int(n_out.value)
 
@@ -111,7 +140,8 @@ class CudaTableBackend:
         from .mash_gpu import GpuSketch
         sk = C.c_void_p()
         info = SketchInfo()
-        torch.cuda.current_stream(self.device).synchronize()
+        if not self.stream_shared:
+            torch.cuda.current_stream(self.device).synchronize()
         check(self.lib.ac_sketch_from_table(self.eng.ctx, hashes.data_ptr(), counts.data_ptr(), hashes.numel(), k, s,
                                             C.byref(sk), C.byref(info)))
         return GpuSketch(self.eng, sk.value, info, name, k, s)
@@ -123,6 +153,8 @@ class ShardedSketcher:
     def __init__(self, engine, rank: int, world: int, group: Optional[dist.ProcessGroup] = None, backend=None):
         self.rank, self.world, self.group = rank, world, group
         self.backend = backend if backend is not None else CudaTableBackend(engine)
+        if hasattr(self.backend, "share_torch_stream"):
+            self.backend.share_torch_stream()
         self.device = self.backend.device
         self.last_exchange = {}
         self._mark = None   # optional callable(name): phase timing hook (tools/time_sharded.py)
@@ -154,29 +186,28 @@ class ShardedSketcher:
         n_q = self.backend.merge_counts(rh, rc, m)
         n_keep = min(n_q, s)
         mark("merge_counts")
-        # -- step 4: gather the owners' prefixes and the job counters
-        meta = torch.tensor([n_keep, n_q, *tab.counters], dtype=torch.int64, device=self.device)
-        metas = torch.empty(P * meta.numel(), dtype=torch.int64, device=self.device)
-        dist.all_gather_into_tensor(metas, meta, group=self.group)
-        metas = metas.view(P, -1).tolist()
-        keeps = [int(r[0]) for r in metas]
-        pad = max(max(keeps), 1)
-        sh = torch.zeros(pad, dtype=torch.int64, device=self.device)
-        sc = torch.zeros(pad, dtype=torch.int32, device=self.device)
-        sh[:n_keep] = rh[:n_keep]
-        sc[:n_keep] = rc[:n_keep]
-        gh = torch.empty(P * pad, dtype=torch.int64, device=self.device)
-        gc = torch.empty(P * pad, dtype=torch.int32, device=self.device)
-        dist.all_gather_into_tensor(gh, sh, group=self.group)
-        dist.all_gather_into_tensor(gc, sc, group=self.group)
+        # -- step 4: ONE all-gather of [header | <= s hashes | <= s counts] per owner (fixed size: no size exchange)
+        HDR = 8
+        pad = max(int(s), 1)
+        words = HDR + pad + (pad + 1) // 2
+        buf = torch.zeros(words, dtype=torch.int64, device=self.device)
+        buf[:HDR] = torch.tensor([n_keep, n_q, *tab.counters, 0], dtype=torch.int64)
+        if n_keep:
+            buf[HDR:HDR + n_keep] = rh[:n_keep]
+            buf[HDR + pad:].view(torch.int32)[:n_keep] = rc[:n_keep]
+        gbuf = torch.empty(P * words, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(gbuf, buf, group=self.group)
+        gbuf = gbuf.view(P, words)
+        metas = gbuf[:, :HDR].tolist()
         mark("all_gather")
+        keeps = [int(r[0]) for r in metas]
         # ordered concatenation (range r < range r+1), first s entries
         parts_h, parts_c, left = [], [], s
         for r in range(P):
             take = min(keeps[r], left)
             if take:
-                parts_h.append(gh[r * pad:r * pad + take])
-                parts_c.append(gc[r * pad:r * pad + take])
+                parts_h.append(gbuf[r, HDR:HDR + take])
+                parts_c.append(gbuf[r, HDR + pad:].view(torch.int32)[:take])
                 left -= take
         if parts_h:
             fh, fc = torch.cat(parts_h).contiguous(), torch.cat(parts_c).contiguous()

@@ -93,6 +93,12 @@ void ac_destroy(ac_ctx *ctx);
 /* Block until everything queued on the context's streams has finished. */
 int ac_sync(ac_ctx *ctx);
 
+/* Run the context's kernels on the caller's CUDA stream (`stream` = a cudaStream_t, `injected` != 0), or go back to
+ * the context's own stream (`injected` = 0).  With an injected stream, entry points that only produce DEVICE-side
+ * results (ac_job_table_export, ac_merge_counts' arrays, ...) are ordered on that stream instead of blocking the host,
+ * so collectives queued on the same stream (NCCL through torch.distributed) need no host synchronisation between them. */
+int ac_set_stream(ac_ctx *ctx, void *stream, int injected);
+
 void *ac_alloc_pinned(size_t n);
 void ac_free_pinned(void *p);
 
