@@ -648,6 +648,26 @@ void launch_table_finish(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, 
     ++*lc.launches;
 }
 
+void launch_table_range_count(const LaunchCtx &lc, const CountTable &ct, const RangeBounds &bounds, JobDev *jd) {
+    cudaMemsetAsync((char *)jd + offsetof(JobDev, range_cnt), 0, sizeof(uint32_t) * MAX_RANGES, lc.stream);
+    k3t_range_count<<<RG_CTAS, RG_THREADS, 0, lc.stream>>>(ct, bounds, jd);
+    ++*lc.launches;
+}
+
+void launch_table_range_scatter(const LaunchCtx &lc, const CountTable &ct, const RangeBounds &bounds, const RangeOffsets &off,
+                                const SelectBufs &sb, JobDev *jd) {
+    cudaMemsetAsync((char *)jd + offsetof(JobDev, range_cnt), 0, sizeof(uint32_t) * MAX_RANGES, lc.stream);   // now the per-range write cursors
+    k3t_range_scatter<<<RG_CTAS, RG_THREADS, 0, lc.stream>>>(ct, bounds, off, jd, sb.tab_hash, sb.tab_cnt);
+    ++*lc.launches;
+}
+
+void launch_merge_insert(const LaunchCtx &lc, const CountTable &ct, const unsigned long long *hashes, const uint32_t *counts,
+                         uint32_t n, JobDev *jd) {
+    if (!n) return;
+    k3t_merge_insert<<<div_up(n, 256), 256, 0, lc.stream>>>(ct, hashes, counts, n, jd);
+    ++*lc.launches;
+}
+
 void launch_finalize(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, int use64) {
     k4_finalize<<<1, 1024, 0, lc.stream>>>(sb.sk_hash, sb.sk_cnt, jd, use64);
     ++*lc.launches;
