@@ -45,6 +45,27 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def bind_to_gpu_numa_node(local: int) -> str:
+    """Pin this rank's threads to the CPUs of its GPU's NUMA node BEFORE the pinned staging memory is allocated
+    (first touch puts the pages there), so H2D copies of N ranks do not all cross the socket interconnect."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        cpus = Path(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read_text().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return f"{bdf} -> cpus {cpus}"
+    except Exception as e:  # no sysfs / attribute: leave the default placement
+        return f"not bound ({type(e).__name__})"
+    return "not bound"
+
+
 # ----------------------------------------------------------------------------- inputs
 def make_reads(n_reads: int, seed: int, tag: int, alloc):
     """C2 reads as 4-line FASTQ text, generated straight into a buffer from `alloc(nbytes)`."""
@@ -244,6 +265,8 @@ def main() -> None:
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device: auriclass_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -266,6 +289,7 @@ def main() -> None:
     dev_text = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
     dev_text.copy_(torch.from_numpy(text), non_blocking=False)
     torch.cuda.synchronize()
+    log(f"[rank {rank}] numa: {numa}")
     log(f"[rank {rank}] generated {args.reads} reads ({nbytes / 1e9:.3f} GB FASTQ) in {time.perf_counter() - t0:.1f} s")
     bases_per_rank = args.reads * READ_LEN
 
@@ -459,7 +483,8 @@ def main() -> None:
             "kernel_ms": {"parse_k1": prof["parse_ms"], "hash_k2": prof["hash_ms"], "select_k3_k4": prof["select_ms"],
                           "job_total": prof["total_ms"]},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # (the contract times the CPU baseline at N = 1 only)
+            os.sched_setaffinity(0, all_cpus)   # the CPU baseline gets every host core again
             out["cpu_baseline"] = cpu_baseline_sample(text, min(args.reads, args.cpu_sample_reads), rec)
         print(json.dumps(out), file=json_out, flush=True)
     if world > 1:
