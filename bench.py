@@ -185,6 +185,8 @@ def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU implementation is entitled to every host core
+    os.environ["OMP_NUM_THREADS"] = os.environ.get("AC_REF_THREADS", str(len(os.sched_getaffinity(0))))
     from auriclass_b200 import synth
     from oracle import oracle
     rec = synth.record_bytes(READ_LEN, 0)
