@@ -413,9 +413,9 @@ def main() -> None:
     # max over ranks
     ms_step = float(np.mean(dev_ms)) if world == 1 else wall_ms
     if world > 1:
-        t = torch.tensor([ms_step, wall_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms_step, wall_ms, e2e_ms, pcie_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step, wall_ms, e2e_ms = [float(x) for x in t.tolist()]
+        ms_step, wall_ms, e2e_ms, pcie_ms = [float(x) for x in t.tolist()]   # pcie floor: all ranks copy at once, slowest rank
 
     if rank == 0:
         peaks = {}
