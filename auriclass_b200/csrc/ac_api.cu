@@ -78,6 +78,8 @@ struct ac_ctx {
     bool profile;
     size_t cand_cap;           // entries in the candidate / sort buffers
     size_t seg_bytes;          // raw text per segment (SEG_BYTES, or AC_SEG_MB for tests)
+    size_t stream_seg_bytes;   // bytes that must be pending before a still-open file is processed (streamed feeds:
+                               // smaller than seg_bytes, so little is left to do when the last chunk arrives)
     SelectBufs sb;
     bool sb_ok;
     CountTable ct;             // count table of speculative passes (key/cnt/qhist owned here; qlist aliases sb.keys_b)
@@ -293,6 +295,7 @@ extern "C" int ac_create(int device, ac_ctx **out) {
     c->seg_bytes = seg_env ? ((size_t)strtoull(seg_env, nullptr, 10) << 20) : SEG_BYTES;
     if (c->seg_bytes < ((size_t)1 << 20)) c->seg_bytes = (size_t)1 << 20;
     if (c->seg_bytes > ((size_t)1 << 30)) c->seg_bytes = (size_t)1 << 30;
+    c->stream_seg_bytes = std::min(c->seg_bytes, SEG_SAFE_BYTES);
     CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
     c->s_own = c->s_comp; c->stream_injected = false;
@@ -599,8 +602,8 @@ static int pump(ac_job *j, bool all) {
         const size_t usable = open ? (avail > HOLD_BACK ? avail - HOLD_BACK : 0) : avail;
         if (open && usable == 0) break;
         if (!all) {
-            if (j->pending < j->ctx->seg_bytes + HOLD_BACK) break;
-            if (open && usable < j->ctx->seg_bytes) break;
+            if (j->pending < j->ctx->stream_seg_bytes + HOLD_BACK) break;
+            if (open && usable < j->ctx->stream_seg_bytes) break;
         }
         if (!j->pass_started) {
             // the size fed so far decides the speculative threshold: big inputs start at 1/16 of
