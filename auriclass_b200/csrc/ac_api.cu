@@ -606,12 +606,13 @@ static int pump(ac_job *j, bool all) {
             if (open && usable < j->ctx->stream_seg_bytes) break;
         }
         if (!j->pass_started) {
-            // the size fed so far decides the speculative threshold: big inputs start at 1/16 of
-            // the hash space, small ones keep everything (tau = max, nothing to verify)
-            // (tau0 = 1/16 must leave >= s qualified hashes: ~128 bytes of text per sketch entry at the least)
+            // the size fed so far decides the speculative threshold: big inputs start at 1/32 of
+            // the hash space (64 expected candidates per 2,048-window sub-tile of K2, half its staging slots),
+            // small ones keep everything (tau = max, nothing to verify)
+            // (tau0 = 1/32 must leave >= s qualified hashes: ~128 bytes of text per sketch entry at the least)
             const size_t spec_min = std::max((size_t)4 << 20, (size_t)128 * (size_t)j->s);
             const bool big = j->pending >= std::min(spec_min, j->ctx->seg_bytes);
-            int rc = start_pass(j, big ? (space_max(j) >> 4) : space_max(j), !big);
+            int rc = start_pass(j, big ? (space_max(j) >> 5) : space_max(j), !big);
             if (rc) return rc;
         }
         const size_t len = std::min(usable, j->safe ? std::min(SEG_SAFE_BYTES, j->ctx->seg_bytes) : j->ctx->seg_bytes);

@@ -14,16 +14,17 @@ constexpr int Z_CARRY = 32;                          // bytes of the base stream
 constexpr size_t SEG_BYTES = 128u << 20;             // raw text per segment: ~13 waves of K2 CTAs, few dependent launches
 constexpr size_t SEG_SAFE_BYTES = 32u << 20;         // segment size when every window may be a candidate (tau = max / safe mode)
 #ifndef AC_K2_THREADS
-#define AC_K2_THREADS 256
+#define AC_K2_THREADS 128
 #endif
 #ifndef AC_K2_MINB
-#define AC_K2_MINB 4
+#define AC_K2_MINB 8
 #endif
-constexpr int K2_THREADS = AC_K2_THREADS;             // hash CTA
-constexpr int K2_W = 32;                             // window starts per hash thread
-constexpr int K2_TILE = K2_THREADS * K2_W;           // window starts per hash CTA
-constexpr int K2_STAGE = K2_TILE / 8;                 // candidate staging slots per hash CTA (shared memory)
-
+constexpr int K2_THREADS = AC_K2_THREADS;             // hash CTA: independent warps, no CTA barrier after the first
+constexpr int K2_WARPS = K2_THREADS / 32;
+constexpr int K2_W = 32;                             // window starts per lane and round
+constexpr int K2_WT = 2048;                          // window starts per hash WARP (its own sub-tile: 64 rounds of 32)
+constexpr int K2_TILE = K2_WARPS * K2_WT;            // window starts per hash CTA
+constexpr int K2_STAGE = 128;                        // candidate staging slots per hash warp (shared memory)
 constexpr int MAX_RANGES = 64;                       // hash ranges (= ranks) of the multi-GPU exchange
 
 enum { FMT_FASTQ = 0, FMT_FASTA = 1 };

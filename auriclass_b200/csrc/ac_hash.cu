@@ -102,206 +102,249 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!ok);
 }
 
-constexpr int K2_TB = K2_TILE + 64;             // tile bytes staged in shared memory (window halo + statistics look-back)
-constexpr int K2_NWV = K2_TILE / 32;            // words of the valid-window bitmap
+constexpr int K2_TB = K2_WT + 64;               // sub-tile bytes staged per warp (window halo + statistics look-back)
+constexpr int K2_NWV = K2_WT / 32;              // words of a warp's valid-window bitmap
+constexpr int K2_ROUNDS = K2_NWV / 32;          // a lane owns word (32 r + lane) in round r
 // group list capacity: two runs are at least K invalid windows apart, a run of L windows makes ceil(L/32) groups
-template <int K> struct K2MaxGroups { static constexpr int value = K2_TILE / (K + 1) + K2_TILE / 32 + 8; };
+template <int K> struct K2MaxGroups { static constexpr int value = K2_WT / (K + 1) + K2_WT / 32 + 8; };
 
+__device__ __forceinline__ uint32_t warp_incl_max(uint32_t v, uint32_t lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, v, d);
+        if (lane >= (uint32_t)d) v = max(v, t);
+    }
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_incl_sum(uint32_t v, uint32_t lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, v, d);
+        if (lane >= (uint32_t)d) v += t;
+    }
+    return v;
+}
+
+// Every WARP owns K2_WT consecutive window starts and works through them on its own: TMA load of its sub-tile,
+// reverse complement + bitmaps, group list, hash loop, record statistics, candidate flush -- synchronised with
+// __syncwarp only.  The prologue / epilogue of one warp (latency bound) thus overlaps the hash loops of the other
+// warps on its sub-partition instead of idling whole CTAs at barriers: with CTA-wide phases only ~64 % of the time
+// enough warps were inside the loop to keep the fmaheavy pipe busy.
 template <int K>
 __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t *__restrict__ Z, JobDev *__restrict__ jd,
                                                          unsigned long long *__restrict__ cand,
                                                          unsigned long long cand_cap, uint32_t seed, int ps_slot,
                                                          const CountTable ct) {
     using Q = ackmer::QuadCfg<K>;
-    __shared__ __align__(128) uint8_t s_fwd[K2_TB + 64];  // base stream bytes of the tile (TMA destination)
-    __shared__ __align__(16) uint8_t s_rc[K2_TB + 64];    // reverse complement of the tile: s_rc[p'] = comp(s_fwd[TB-1-p'])
-    __shared__ uint32_t s_valid[K2_TB / 32 + 2];          // bit b of word c: byte 32c+b is a valid base
-    __shared__ uint32_t s_sep[K2_TB / 32 + 2];            // ... is a record separator
-    __shared__ uint32_t s_wv[K2_NWV + 1];                 // bit b of word c: a k-mer to hash starts at byte 32c+b ([K2_NWV] = 0)
     constexpr int K2_MAXG = K2MaxGroups<K>::value;
-    __shared__ uint16_t s_groups[K2_MAXG];                // start positions of the groups of <= 32 consecutive valid windows
-    __shared__ uint32_t s_ngroups;
-    __shared__ uint32_t s_scan[33];
-    __shared__ SinkShared s_sink;
-    __shared__ unsigned long long s_base;
-    __shared__ unsigned long long s_stat[5];  // kmers, records, kept, short_len, bases
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(128) uint8_t s_fwd_all[K2_WARPS][K2_TB + 64];  // base stream bytes of the sub-tile (TMA destination)
+    __shared__ __align__(16) uint8_t s_rc_all[K2_WARPS][K2_TB + 64];    // its reverse complement: rc[p'] = comp(fwd[TB-1-p'])
+    __shared__ uint32_t s_valid_all[K2_WARPS][K2_TB / 32 + 2];          // bit b of word c: byte 32c+b is a valid base
+    __shared__ uint32_t s_sep_all[K2_WARPS][K2_TB / 32 + 2];            // ... is a record separator
+    __shared__ uint32_t s_wv_all[K2_WARPS][K2_NWV + 1];                 // bit b of word c: a k-mer to hash starts at byte 32c+b
+    __shared__ uint16_t s_groups_all[K2_WARPS][K2_MAXG];                // start positions of the groups of <= 32 consecutive valid windows
+    __shared__ SinkShared s_sink_all[K2_WARPS];
+    __shared__ __align__(8) uint64_t s_bar_all[K2_WARPS];
+    __shared__ unsigned long long s_stat[6];  // kmers, records, kept, short_len, bases, candidates: summed over the CTA's warps
+    __shared__ uint32_t s_done;               // warps that have finished; the last one adds s_stat to the job counters
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 6) s_stat[tid] = 0;
+    if (tid == 0) s_done = 0;
+    __syncthreads();   // the only CTA barrier: every warp is still at its first instruction
 
     const uint32_t n_zbuf = jd->ps[ps_slot].n_zbuf, z_begin = jd->ps[ps_slot].z_begin;
     const long long n_win = (long long)n_zbuf - K + 1;             // window starts 0 .. n_win-1 exist
-    const long long tile_start = (long long)blockIdx.x * K2_TILE;
-    // a tile is needed while it holds window starts; record-end positions p = start + K < n_zbuf
-    // always belong to such a tile (p - K <= n_win - 2)
-    if (tile_start >= n_win) return;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        s_ngroups = 0; s_wv[K2_NWV] = 0;
-        s_sink.cnt = 0; s_sink.tau = jd->tau;
-        s_sink.cand = cand; s_sink.cand_count = &jd->cand_count; s_sink.cand_cap = cand_cap;
-        s_sink.overflow = &jd->overflow; s_sink.jd = jd; s_sink.ct = ct;
-        mbar_init(&s_bar, 1);
-    }
-    if (tid < 5) s_stat[tid] = 0;
-    __syncthreads();
-    if (tid == 0) tma_load_1d(s_fwd, Z + tile_start, K2_TB, &s_bar);
-    mbar_wait(&s_bar, 0);
+    const long long tile_start = ((long long)blockIdx.x * K2_WARPS + warp) * K2_WT;
+    uint32_t nk = 0, n_rec = 0, n_kept = 0, short_len = 0, n_bases = 0, n_emitted = 0;
 
-    // ---- once per CTA: reverse-complement tile + validity / separator bitmaps (chunk = 32 bytes)
-    for (uint32_t c = tid; c < K2_TB / 32; c += K2_THREADS) {
-        uint32_t w[8];
-        const uint4 a = reinterpret_cast<const uint4 *>(s_fwd)[2 * c], b4 = reinterpret_cast<const uint4 *>(s_fwd)[2 * c + 1];
-        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b4.x; w[5] = b4.y; w[6] = b4.z; w[7] = b4.w;
-        uint32_t vm = 0, sm = 0, rcw[8];
+    // a sub-tile is needed while it holds window starts; record-end positions p = start + K < n_zbuf
+    // always belong to such a sub-tile (p - K <= n_win - 2)
+    if (tile_start < n_win) {
+        uint8_t *s_fwd = s_fwd_all[warp], *s_rc = s_rc_all[warp];
+        uint32_t *s_valid = s_valid_all[warp], *s_sep = s_sep_all[warp], *s_wv = s_wv_all[warp];
+        uint16_t *s_groups = s_groups_all[warp];
+        SinkShared &s_sink = s_sink_all[warp];
+        uint64_t *s_bar = &s_bar_all[warp];
+        if (lane == 0) {
+            s_wv[K2_NWV] = 0;
+            s_sink.cnt = 0; s_sink.tau = jd->tau;
+            s_sink.cand = cand; s_sink.cand_count = &jd->cand_count; s_sink.cand_cap = cand_cap;
+            s_sink.overflow = &jd->overflow; s_sink.jd = jd; s_sink.ct = ct;
+            mbar_init(s_bar, 1);
+        }
+        __syncwarp();
+        if (lane == 0) tma_load_1d(s_fwd, Z + tile_start, K2_TB, s_bar);
+        mbar_wait(s_bar, 0);
+
+        // ---- once per sub-tile: reverse complement + validity / separator bitmaps (chunk = 32 bytes)
+        for (uint32_t c = lane; c < K2_TB / 32; c += 32) {
+            uint32_t w[8];
+            const uint4 a = reinterpret_cast<const uint4 *>(s_fwd)[2 * c], b4 = reinterpret_cast<const uint4 *>(s_fwd)[2 * c + 1];
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b4.x; w[5] = b4.y; w[6] = b4.z; w[7] = b4.w;
+            uint32_t vm = 0, sm = 0, rcw[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            vm |= ackmer::valid_nibble(w[j]) << (4 * j);
-            const uint32_t nz = ((w[j] >> 6) | w[j]) & 0x01010101u;
-            sm |= (((nz * 0x01020408u) >> 24) ^ 0xFu) << (4 * j);
-            rcw[7 - j] = __byte_perm(ackmer::comp4(w[j]), 0, 0x0123);
+            for (int j = 0; j < 8; j++) {
+                vm |= ackmer::valid_nibble(w[j]) << (4 * j);
+                const uint32_t nz = ((w[j] >> 6) | w[j]) & 0x01010101u;
+                sm |= (((nz * 0x01020408u) >> 24) ^ 0xFu) << (4 * j);
+                rcw[7 - j] = __byte_perm(ackmer::comp4(w[j]), 0, 0x0123);
+            }
+            s_valid[c] = vm; s_sep[c] = sm;
+            uint4 *dst = reinterpret_cast<uint4 *>(s_rc + (K2_TB - 32 * (c + 1)));
+            dst[0] = make_uint4(rcw[0], rcw[1], rcw[2], rcw[3]);
+            dst[1] = make_uint4(rcw[4], rcw[5], rcw[6], rcw[7]);
         }
-        s_valid[c] = vm; s_sep[c] = sm;
-        uint4 *dst = reinterpret_cast<uint4 *>(s_rc + (K2_TB - 32 * (c + 1)));
-        dst[0] = make_uint4(rcw[0], rcw[1], rcw[2], rcw[3]);
-        dst[1] = make_uint4(rcw[4], rcw[5], rcw[6], rcw[7]);
-    }
-    __syncthreads();
+        __syncwarp();
 
-    // ---- valid-window bitmap: thread t owns window starts 32t .. 32t+31 of the tile
-    const long long run_start = tile_start + (long long)tid * K2_W;
-    // windows allowed by the stream range: first unprocessed start is z_begin-(K-1) (earlier ones were
-    // hashed with the previous segment), last is n_win-1
-    long long wlo = (long long)z_begin - (K - 1) - run_start, whi = n_win - run_start;
-    wlo = wlo < 0 ? 0 : wlo; whi = whi > K2_W ? K2_W : whi;
-    uint32_t win_ok = 0;
-    if (whi > wlo) win_ok = (whi >= 32 ? 0xffffffffu : ((1u << whi) - 1u)) & ~((1u << wlo) - 1u);
-    const uint64_t vm64 = (uint64_t)s_valid[tid] | ((uint64_t)s_valid[tid + 1] << 32);
-    const uint32_t vmask = (uint32_t)ackmer::windows_all_valid<K>(vm64) & win_ok;
-    s_wv[tid] = vmask;
-
-    // ---- group list.  Runs of valid windows are cut every 32 windows counted from the run's start, so a
-    // run continuing from the previous word puts a cut at bit (its start position mod 32) of this word.
-    {
-        const uint32_t prev_last = __shfl_up_sync(FULL, vmask >> 31, 1);
-        if (lane == 31) s_scan[warp] = vmask >> 31;   // (block_incl_max below syncs before s_scan is reused)
-        __syncthreads();
-        const bool cont = (vmask & 1u) && (lane ? prev_last : (warp ? s_scan[warp - 1] : 0u));  // tile start = fresh run
-        __syncthreads();
-        const uint32_t starts = vmask & ~((vmask << 1) | (cont ? 1u : 0u));
-        // start bit of the run that reaches the end of this word (0 = this word passes an older run through / no run)
-        uint32_t enc = 0;
-        if ((vmask >> 31) && starts) enc = ((tid + 1u) << 5) | (31u - __clz(starts));
-        const uint32_t inc = block_incl_max<K2_THREADS>(enc, s_scan);
-        uint32_t before = __shfl_up_sync(FULL, inc, 1);
-        if (lane == 31) s_scan[warp] = inc;
-        __syncthreads();
-        if (lane == 0) before = warp ? s_scan[warp - 1] : 0u;
-        uint32_t extra = 0xffffffffu;                  // cut of the continuing run inside this word, if any
-        if (cont) {
-            const uint32_t phi = before & 31u;         // before != 0: the run started at some word's start bit
-            const uint32_t ones = (vmask == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~vmask) - 1);
-            if (phi < ones && phi != 0u) extra = phi;  // phi == 0: the run started at bit 0 of a word, its cut is bit 0 here
-            else if (phi == 0u) extra = 0u;
-        }
-        const uint32_t n_mine = __popc(starts) + (extra != 0xffffffffu ? 1u : 0u);
-        if (n_mine) {
-            uint32_t slot = atomicAdd(&s_ngroups, n_mine);
-            if (extra != 0xffffffffu) { if (slot < K2_MAXG) s_groups[slot] = (uint16_t)(32u * tid + extra); slot++; }
-            for (uint32_t st = starts; st; st &= st - 1, slot++)
-                if (slot < K2_MAXG) s_groups[slot] = (uint16_t)(32u * tid + (uint32_t)(__ffs(st) - 1));
-        }
-    }
-    __syncthreads();
-    const uint32_t n_groups = s_ngroups;
-    if (n_groups > (uint32_t)K2_MAXG) __trap();  // cannot happen (see K2MaxGroups)
-
-    CandSink<(K > 16)> sink;
-    {
-        const unsigned long long tau = s_sink.tau;
-        const uint32_t top = (uint32_t)(tau >> 32);
-        sink.gate = (K > 16) ? (top == 0xffffffffu ? top : top + 1u) : (uint32_t)tau;
-        sink.ss = &s_sink;
-    }
-    const ackmer::MurmurConsts mc;   // (registers are too scarce to hide these from ptxas' constant folding: 64/thread at 4 CTAs/SM)
-
-    // ---- hash: a quad per group, lane c takes windows g+c+4j
-    {
-        const uint32_t quad = lane >> 2, c = lane & 3u;
-        const uint32_t *fwd_w = reinterpret_cast<const uint32_t *>(s_fwd);
-        const uint32_t *rc_w = reinterpret_cast<const uint32_t *>(s_rc);
+        // ---- valid-window bitmap and group list.  Runs of valid windows are cut every 32 windows counted from the
+        // run's start, so a run continuing from the previous word puts a cut at bit (its start position mod 32) of
+        // this word.  Lane l owns word 32 r + l in round r; the run state is carried from round to round.
+        uint32_t n_groups = 0, carry_last = 0, carry_enc = 0;
 #pragma unroll 1
-        for (uint32_t gi = warp * 8u + quad; gi < n_groups; gi += (K2_THREADS / 32) * 8u) {
-            const uint32_t g = s_groups[gi];
-            // the 32 windows from g on, restricted to the run that starts at g (a later run has its own group)
-            uint32_t vb = __funnelshift_r(s_wv[g >> 5], s_wv[(g >> 5) + 1], g & 31u);
-            vb &= ~(vb + 1u);
-            vb >>= c;
-            const uint32_t A = g + c;                                  // byte of the lane's window 0
-            const uint32_t QL = (uint32_t)(K2_TB - K) - A - 4u * (Q::G - 1);  // byte where its window G-1's reverse complement starts
-            uint32_t in[Q::NL], fw[Q::NS], rw[Q::NS];
-#pragma unroll
-            for (int i = 0; i < Q::NL; i++) in[i] = fwd_w[(A >> 2) + i];
-            ackmer::preshift<Q::NS>(in, A & 3u, fw);
-#pragma unroll
-            for (int i = 0; i < Q::NL; i++) in[i] = rc_w[(QL >> 2) + i];
-            ackmer::preshift<Q::NS>(in, QL & 3u, rw);
-            ackmer::process_quad_windows<K, 0>(fw, rw, vb, seed, mc, sink);
-        }
-    }
+        for (int r = 0; r < K2_ROUNDS; r++) {
+            const uint32_t wi = 32u * r + lane;
+            const long long run_start = tile_start + (long long)wi * K2_W;
+            // windows allowed by the stream range: first unprocessed start is z_begin-(K-1) (earlier ones were
+            // hashed with the previous segment), last is n_win-1
+            long long wlo = (long long)z_begin - (K - 1) - run_start, whi = n_win - run_start;
+            wlo = wlo < 0 ? 0 : wlo; whi = whi > K2_W ? K2_W : whi;
+            uint32_t win_ok = 0;
+            if (whi > wlo) win_ok = (whi >= 32 ? 0xffffffffu : ((1u << whi) - 1u)) & ~((1u << wlo) - 1u);
+            const uint64_t vm64 = (uint64_t)s_valid[wi] | ((uint64_t)s_valid[wi + 1] << 32);
+            const uint32_t vmask = (uint32_t)ackmer::windows_all_valid<K>(vm64) & win_ok;
+            s_wv[wi] = vmask;
+            nk += __popc(vmask);
 
-    // ---- record statistics (Mash skips records shorter than k; FASTA `length` = sum of kept lengths)
-    // positions j in [K, K+W) of the run <-> stream positions p = run_start + j in [z_begin, n_zbuf)
-    uint32_t n_rec = 0, n_kept = 0, short_len = 0, n_bases = 0;
-    {
-        const uint64_t sep = (uint64_t)s_sep[tid] | ((uint64_t)s_sep[tid + 1] << 32);
-        long long plo = (long long)z_begin - run_start, phi = (long long)n_zbuf - run_start;
-        plo = plo < K ? K : plo; phi = phi > K + K2_W ? K + K2_W : phi;
-        if (phi > plo) {
-            const uint64_t range = ((phi >= 64) ? ~0ULL : ((1ULL << phi) - 1ULL)) & ~((1ULL << plo) - 1ULL);
-            n_bases = __popcll(~sep & range);
-            uint64_t todo = sep & range;
-            while (todo) {
-                const int j = __ffsll((long long)todo) - 1;
-                todo &= todo - 1;
-                const uint64_t back = sep & (((1ULL << j) - 1ULL) & ~((1ULL << (j - K)) - 1ULL));  // bytes j-K .. j-1
-                if (back == 0) { n_rec++; n_kept++; }
-                else {
-                    const int pj = 63 - __clzll((long long)back);
-                    const int L = j - pj - 1;
-                    if (L > 0) { n_rec++; short_len += L; }
+            uint32_t prev_last = __shfl_up_sync(FULL, vmask >> 31, 1);
+            if (lane == 0) prev_last = carry_last;                       // sub-tile start = fresh run (carry_last = 0)
+            const bool cont = (vmask & 1u) && prev_last;
+            const uint32_t starts = vmask & ~((vmask << 1) | (cont ? 1u : 0u));
+            // start bit of the run that reaches the end of this word (0 = this word passes an older run through / no run)
+            uint32_t enc = 0;
+            if ((vmask >> 31) && starts) enc = ((wi + 1u) << 5) | (31u - __clz(starts));
+            const uint32_t inc = max(warp_incl_max(enc, lane), carry_enc);
+            uint32_t before = __shfl_up_sync(FULL, inc, 1);
+            if (lane == 0) before = carry_enc;
+            uint32_t extra = 0xffffffffu;                  // cut of the continuing run inside this word, if any
+            if (cont) {
+                const uint32_t phi = before & 31u;         // before != 0: the run started at some word's start bit
+                const uint32_t ones = (vmask == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~vmask) - 1);
+                if (phi < ones && phi != 0u) extra = phi;  // phi == 0: the run started at bit 0 of a word, its cut is bit 0 here
+                else if (phi == 0u) extra = 0u;
+            }
+            const uint32_t n_mine = __popc(starts) + (extra != 0xffffffffu ? 1u : 0u);
+            const uint32_t incl = warp_incl_sum(n_mine, lane);
+            uint32_t slot = n_groups + incl - n_mine;
+            if (extra != 0xffffffffu) { if (slot < K2_MAXG) s_groups[slot] = (uint16_t)(32u * wi + extra); slot++; }
+            for (uint32_t st = starts; st; st &= st - 1, slot++)
+                if (slot < K2_MAXG) s_groups[slot] = (uint16_t)(32u * wi + (uint32_t)(__ffs(st) - 1));
+            n_groups += __shfl_sync(FULL, incl, 31);
+            carry_last = __shfl_sync(FULL, vmask >> 31, 31);
+            carry_enc = __shfl_sync(FULL, inc, 31);
+        }
+        __syncwarp();
+        if (n_groups > (uint32_t)K2_MAXG) __trap();  // cannot happen (see K2MaxGroups)
+
+        CandSink<(K > 16)> sink;
+        {
+            const unsigned long long tau = s_sink.tau;
+            const uint32_t top = (uint32_t)(tau >> 32);
+            sink.gate = (K > 16) ? (top == 0xffffffffu ? top : top + 1u) : (uint32_t)tau;
+            sink.ss = &s_sink;
+        }
+        const ackmer::MurmurConsts mc;   // (registers are too scarce to hide these from ptxas' constant folding: 64/thread)
+
+        // ---- hash: a quad per group, lane c takes windows g+c+4j
+        {
+            const uint32_t quad = lane >> 2, c = lane & 3u;
+            const uint32_t *fwd_w = reinterpret_cast<const uint32_t *>(s_fwd);
+            const uint32_t *rc_w = reinterpret_cast<const uint32_t *>(s_rc);
+#pragma unroll 1
+            for (uint32_t gi = quad; gi < n_groups; gi += 8u) {
+                const uint32_t g = s_groups[gi];
+                // the 32 windows from g on, restricted to the run that starts at g (a later run has its own group)
+                uint32_t vb = __funnelshift_r(s_wv[g >> 5], s_wv[(g >> 5) + 1], g & 31u);
+                vb &= ~(vb + 1u);
+                vb >>= c;
+                const uint32_t A = g + c;                                  // byte of the lane's window 0
+                const uint32_t QL = (uint32_t)(K2_TB - K) - A - 4u * (Q::G - 1);  // byte where its window G-1's reverse complement starts
+                uint32_t in[Q::NL], fw[Q::NS], rw[Q::NS];
+#pragma unroll
+                for (int i = 0; i < Q::NL; i++) in[i] = fwd_w[(A >> 2) + i];
+                ackmer::preshift<Q::NS>(in, A & 3u, fw);
+#pragma unroll
+                for (int i = 0; i < Q::NL; i++) in[i] = rc_w[(QL >> 2) + i];
+                ackmer::preshift<Q::NS>(in, QL & 3u, rw);
+                ackmer::process_quad_windows<K, 0>(fw, rw, vb, seed, mc, sink);
+            }
+        }
+
+        // ---- record statistics (Mash skips records shorter than k; FASTA `length` = sum of kept lengths)
+        // positions j in [K, K+W) of the run <-> stream positions p = run_start + j in [z_begin, n_zbuf)
+#pragma unroll 1
+        for (int r = 0; r < K2_ROUNDS; r++) {
+            const uint32_t wi = 32u * r + lane;
+            const long long run_start = tile_start + (long long)wi * K2_W;
+            const uint64_t sep = (uint64_t)s_sep[wi] | ((uint64_t)s_sep[wi + 1] << 32);
+            long long plo = (long long)z_begin - run_start, phi = (long long)n_zbuf - run_start;
+            plo = plo < K ? K : plo; phi = phi > K + K2_W ? K + K2_W : phi;
+            if (phi > plo) {
+                const uint64_t range = ((phi >= 64) ? ~0ULL : ((1ULL << phi) - 1ULL)) & ~((1ULL << plo) - 1ULL);
+                n_bases += __popcll(~sep & range);
+                uint64_t todo = sep & range;
+                while (todo) {
+                    const int j = __ffsll((long long)todo) - 1;
+                    todo &= todo - 1;
+                    const uint64_t back = sep & (((1ULL << j) - 1ULL) & ~((1ULL << (j - K)) - 1ULL));  // bytes j-K .. j-1
+                    if (back == 0) { n_rec++; n_kept++; }
+                    else {
+                        const int pj = 63 - __clzll((long long)back);
+                        const int L = j - pj - 1;
+                        if (L > 0) { n_rec++; short_len += L; }
+                    }
                 }
             }
         }
+
+        // ---- candidates of this sub-tile
+        __syncwarp();
+        n_emitted = s_sink.cnt;
+        const uint32_t n_staged = min(n_emitted, (uint32_t)K2_STAGE);
+        if (ct.mask) {   // count-table mode: one insertion per staged candidate
+            for (uint32_t i = lane; i < n_staged; i += 32) ct_insert(ct, s_sink.buf[i], jd);
+        } else if (n_staged) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&jd->cand_count, (unsigned long long)n_staged);
+            base = __shfl_sync(FULL, base, 0);
+            for (uint32_t i = lane; i < n_staged; i += 32) {
+                const unsigned long long g = base + i;
+                if (g < cand_cap) cand[g] = s_sink.buf[i]; else jd->overflow = 1u;
+            }
+        }
     }
-    uint32_t nk = __popc(vmask);
+
+    // ---- job counters: warp -> CTA (shared atomics) -> one set of global atomics by the CTA's last warp
     nk = __reduce_add_sync(FULL, nk); n_rec = __reduce_add_sync(FULL, n_rec); n_kept = __reduce_add_sync(FULL, n_kept);
     short_len = __reduce_add_sync(FULL, short_len); n_bases = __reduce_add_sync(FULL, n_bases);
-    if ((tid & 31) == 0) {
+    if (lane == 0) {
         if (nk) atomicAdd(&s_stat[0], (unsigned long long)nk);
         if (n_rec) atomicAdd(&s_stat[1], (unsigned long long)n_rec);
         if (n_kept) atomicAdd(&s_stat[2], (unsigned long long)n_kept);
         if (short_len) atomicAdd(&s_stat[3], (unsigned long long)short_len);
         if (n_bases) atomicAdd(&s_stat[4], (unsigned long long)n_bases);
-    }
-    __syncthreads();
-    const uint32_t n_emitted = s_sink.cnt, n_staged = min(n_emitted, (uint32_t)K2_STAGE);
-    if (tid == 0) {
-        if (s_stat[0]) atomicAdd(&jd->n_kmers, s_stat[0]);
-        if (s_stat[1]) atomicAdd(&jd->n_records, s_stat[1]);
-        if (s_stat[2]) atomicAdd(&jd->n_kept, s_stat[2]);
-        if (s_stat[3]) atomicAdd(&jd->n_short_len, s_stat[3]);
-        if (s_stat[4]) atomicAdd(&jd->n_bases, s_stat[4]);
-        if (n_emitted) atomicAdd(&jd->cand_total, (unsigned long long)n_emitted);
-        s_base = (n_staged && !ct.mask) ? atomicAdd(&jd->cand_count, (unsigned long long)n_staged) : 0ULL;
-    }
-    if (ct.mask) {   // count-table mode: one insertion per staged candidate, the whole CTA in parallel
-        for (uint32_t i = tid; i < n_staged; i += K2_THREADS) ct_insert(ct, s_sink.buf[i], jd);
-        return;
-    }
-    __syncthreads();
-    const unsigned long long base = s_base;
-    for (uint32_t i = tid; i < n_staged; i += K2_THREADS) {
-        const unsigned long long g = base + i;
-        if (g < cand_cap) cand[g] = s_sink.buf[i]; else jd->overflow = 1u;
+        if (n_emitted) atomicAdd(&s_stat[5], (unsigned long long)n_emitted);
+        __threadfence_block();
+        if (atomicAdd(&s_done, 1u) == (uint32_t)K2_WARPS - 1u) {
+            __threadfence_block();
+            const volatile unsigned long long *st = s_stat;
+            if (st[0]) atomicAdd(&jd->n_kmers, st[0]);
+            if (st[1]) atomicAdd(&jd->n_records, st[1]);
+            if (st[2]) atomicAdd(&jd->n_kept, st[2]);
+            if (st[3]) atomicAdd(&jd->n_short_len, st[3]);
+            if (st[4]) atomicAdd(&jd->n_bases, st[4]);
+            if (st[5]) atomicAdd(&jd->cand_total, st[5]);
+        }
     }
 }
 
