@@ -190,51 +190,54 @@ __device__ void d_finish_pair(u64 common, u64 denom, int k, u64 len_a, u64 len_b
     *o_dist = d; *o_p = pv;
 }
 
-// ---- K5 for tiles of pairs (all-vs-all `mash dist`, BASELINE config 5): merge path, one warp per pair.
-// The merged sequence of the two ascending lists (ties: the A element first, its B twin right behind it) is cut
-// into 32 equal diagonal ranges; a lane finds its start by binary search along the diagonal, walks its range
-// and counts distinct values and twins.  Mash's capped merge (App. A.6) stops at the S-th distinct value and
-// counts a twin of that value too, so: common = twins whose rank (distinct values up to and including their
-// A twin) is <= S, denom = min(S, distinct).  Only diagonals below 2S + 1 can matter.
-constexpr int P_WARPS = 8;   // pairs per CTA
+// ---- K5 for tiles of pairs (all-vs-all `mash dist`, BASELINE config 5): blocked merge path, one warp per pair.
+// The merged sequence of the two ascending lists (ties: the A element first, its B twin right behind it) is
+// consumed in blocks of P_BLOCK items.  Per block the warp stages the next P_BLOCK hashes of either list in
+// shared memory with coalesced loads, every lane finds its diagonal range by binary search (merge path) and walks
+// it from shared memory counting distinct values and twins; a warp scan turns the lane counts into ranks.
+// Mash's capped merge (App. A.6) stops at the S-th distinct value and counts a twin of that value too, so:
+// common = twins whose rank (distinct values up to and including their A twin) is <= S, denom = min(S, distinct).
+// The walk ends as soon as the cap is reached or one list is exhausted -- the rest only adds to `distinct`.
+constexpr int P_WARPS = 4;      // pairs per CTA
+constexpr int P_BLOCK = 512;    // merged items per block and warp (2 x 4 KB of shared memory per warp)
 
 struct PathPos { uint32_t i, j; };
 
-__device__ __forceinline__ PathPos merge_path_split(const u64 *__restrict__ A, uint32_t nA, const u64 *__restrict__ B,
-                                                   uint32_t nB, uint32_t d) {
-    uint32_t lo = d > nB ? d - nB : 0u, hi = d < nA ? d : nA;
+// split of diagonal d of the merge of a[0..na) and b[0..nb): i items of a and d - i of b come first
+__device__ __forceinline__ PathPos merge_path_split(const u64 *a, uint32_t na, const u64 *b, uint32_t nb, uint32_t d) {
+    uint32_t lo = d > nb ? d - nb : 0u, hi = d < na ? d : na;
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        // A[mid] <= B[d - mid - 1]: A[mid] is merged before that B element, the split lies further right
-        if (A[mid] <= B[d - mid - 1]) lo = mid + 1; else hi = mid;
+        // a[mid] <= b[d - mid - 1]: a[mid] is merged before that b element, the split lies further right
+        if (a[mid] <= b[d - mid - 1]) lo = mid + 1; else hi = mid;
     }
     return PathPos{lo, d - lo};
 }
 
-// walks items [pos, pos + len) of the merged sequence; returns distinct values, and twins whose rank
-// (rank_before + distinct values so far in this range) is <= S
-__device__ __forceinline__ void merge_walk(const u64 *__restrict__ A, uint32_t nA, const u64 *__restrict__ B, uint32_t nB,
-                                           PathPos p, uint32_t len, u64 rank_before, u64 S, uint32_t &distinct,
-                                           uint32_t &twins_in) {
+// walks items [pos, pos + len) of the merged sequence; prev_a: the A value merged just before a[0] (valid iff have_prev)
+// counts distinct values, A items taken, and twins whose rank (rank_before + distinct so far) is <= S
+__device__ __forceinline__ void merge_walk(const u64 *a, uint32_t na, const u64 *b, uint32_t nb, PathPos p, uint32_t len,
+                                           u64 prev_a, bool have_prev, u64 rank_before, u64 S, uint32_t &distinct,
+                                           uint32_t &twins_in, uint32_t &a_taken) {
     uint32_t i = p.i, j = p.j, dist = 0, tw = 0;
-    u64 a = i < nA ? A[i] : ~0ULL, b = j < nB ? B[j] : ~0ULL;
-    u64 last_a = i > 0 ? A[i - 1] : 0ULL;
-    bool have_last = i > 0;
+    u64 av = i < na ? a[i] : ~0ULL, bv = j < nb ? b[j] : ~0ULL;
+    u64 last_a = i > 0 ? a[i - 1] : prev_a;
+    bool have_last = i > 0 || have_prev;
     for (uint32_t t = 0; t < len; t++) {
-        const bool take_a = (j >= nB) || (i < nA && a <= b);
+        const bool take_a = (j >= nb) || (i < na && av <= bv);
         if (take_a) {
             dist++;
-            last_a = a; have_last = true;
+            last_a = av; have_last = true;
             i++;
-            a = i < nA ? A[i] : ~0ULL;
+            av = i < na ? a[i] : ~0ULL;
         } else {
-            if (have_last && b == last_a) { if (rank_before + dist <= S) tw++; }   // twin of the A element just merged
+            if (have_last && bv == last_a) { if (rank_before + dist <= S) tw++; }   // twin of the A element just merged
             else dist++;
             j++;
-            b = j < nB ? B[j] : ~0ULL;
+            bv = j < nb ? b[j] : ~0ULL;
         }
     }
-    distinct = dist; twins_in = tw;
+    distinct = dist; twins_in = tw; a_taken = i - p.i;
 }
 
 __global__ void __launch_bounds__(P_WARPS * 32) k5_pairs(const u64 *__restrict__ a_hashes, const u64 *__restrict__ a_off,
@@ -243,37 +246,69 @@ __global__ void __launch_bounds__(P_WARPS * 32) k5_pairs(const u64 *__restrict__
                                                          const u64 *__restrict__ b_len, uint32_t j0, uint32_t nj, int k, u64 S,
                                                          double *__restrict__ o_dist, double *__restrict__ o_p,
                                                          u64 *__restrict__ o_common, u64 *__restrict__ o_denom) {
-    const uint32_t lane = threadIdx.x & 31;
-    const u64 pair = (u64)blockIdx.x * P_WARPS + (threadIdx.x >> 5);
+    __shared__ u64 s_a_all[P_WARPS][P_BLOCK], s_b_all[P_WARPS][P_BLOCK];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 pair = (u64)blockIdx.x * P_WARPS + warp;
     if (pair >= (u64)ni * nj) return;
+    u64 *sa = s_a_all[warp], *sb = s_b_all[warp];
     const uint32_t ia = i0 + (uint32_t)(pair / nj), jb = j0 + (uint32_t)(pair % nj);
     const u64 *A = a_hashes + a_off[ia];
     const uint32_t nA = (uint32_t)(a_off[ia + 1] - a_off[ia]);
     const u64 *B = b_hashes + b_off[jb];
     const uint32_t nB = (uint32_t)(b_off[jb + 1] - b_off[jb]);
-    const u64 total = (u64)nA + nB;
-    const uint32_t L = (uint32_t)(total < 2 * S + 1 ? total : 2 * S + 1);   // diagonals that can matter
-    const uint32_t per = (L + 31) / 32;
-    const uint32_t d0 = min(lane * per, L), d1 = min(d0 + per, L);
-    const PathPos p = merge_path_split(A, nA, B, nB, d0);
-    // pass 1: distinct values per lane (rank_before = 0 and S = max: every twin counts)
-    uint32_t distinct, twins_all;
-    merge_walk(A, nA, B, nB, p, d1 - d0, 0, ~0ULL, distinct, twins_all);
-    uint32_t inc = distinct;
+
+    uint32_t ci = 0, cj = 0;        // items of A / B consumed so far
+    u64 rank = 0, common = 0;       // distinct values so far, twins of rank <= S so far
+    u64 prev_a = 0;                 // last A value consumed (valid iff ci > 0)
+    u64 uni = 0;                    // distinct values of the whole union, or any value >= S once the cap is known to decide
+    for (;;) {
+        if (ci == nA || cj == nB) {
+            // one list is exhausted: what is left of the other is all distinct, except a leading twin of prev_a
+            uint32_t tw = 0;
+            if (ci == nA && cj < nB && ci > 0 && B[cj] == prev_a) tw = 1;
+            if (tw && rank <= S) common += 1;
+            uni = rank + (u64)(nA - ci) + (u64)(nB - cj) - tw;
+            break;
+        }
+        const uint32_t na = min((uint32_t)P_BLOCK, nA - ci), nb = min((uint32_t)P_BLOCK, nB - cj);
+        for (uint32_t t = lane; t < na; t += 32) sa[t] = A[ci + t];
+        for (uint32_t t = lane; t < nb; t += 32) sb[t] = B[cj + t];
+        __syncwarp();
+        const uint32_t D = min((uint32_t)P_BLOCK, na + nb);   // the first D merged items only involve the staged values
+        const uint32_t per = (D + 31) / 32;
+        const uint32_t d0 = min(lane * per, D), d1 = min(d0 + per, D);
+        const PathPos p = merge_path_split(sa, na, sb, nb, d0);
+        uint32_t distinct, twins, a_taken;
+        merge_walk(sa, na, sb, nb, p, d1 - d0, prev_a, ci > 0, 0, ~0ULL, distinct, twins, a_taken);
+        uint32_t inc = distinct;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(FULL, inc, d);
-        if (lane >= d) inc += t;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, inc, d);
+            if (lane >= (uint32_t)d) inc += t;
+        }
+        const uint32_t block_distinct = __shfl_sync(FULL, inc, 31);
+        if (rank + block_distinct > S) {
+            // the cap falls inside this block: twins count only up to rank S, and the walk is over
+            uint32_t d2, tw2, a2;
+            merge_walk(sa, na, sb, nb, p, d1 - d0, prev_a, ci > 0, rank + (inc - distinct), S, d2, tw2, a2);
+            common += __reduce_add_sync(FULL, tw2);
+            uni = rank + block_distinct;    // > S: the cap decides denom
+            break;
+        }
+        common += __reduce_add_sync(FULL, twins);
+        rank += block_distinct;
+        const uint32_t a_used = __reduce_add_sync(FULL, a_taken);
+        if (a_used) prev_a = sa[a_used - 1];
+        ci += a_used; cj += D - a_used;
+        __syncwarp();                       // the staging buffers are rewritten by the next block
+        if (rank == S) {
+            // cap reached exactly at the block's end: only a twin of the last value could still count
+            if (cj < nB && ci > 0 && B[cj] == prev_a) common += 1;
+            uni = rank + ((ci < nA || cj < nB) ? 1 : 0);   // >= S either way
+            break;
+        }
     }
-    const u64 before = inc - distinct;
-    const u64 uni = __shfl_sync(FULL, inc, 31);
-    // pass 2 only where the cap cuts through the lane's range
-    uint32_t twins_in;
-    if (before + distinct <= S) twins_in = twins_all;
-    else merge_walk(A, nA, B, nB, p, d1 - d0, before, S, distinct, twins_in);
-    const u64 common = __reduce_add_sync(FULL, twins_in);
     if (lane == 0) {
-        // diagonals beyond L were not walked: then uni >= S already, so the cap decides
         const u64 denom = uni < S ? uni : S;
         d_finish_pair(common, denom, k, a_len[ia], b_len[jb], o_dist + pair, o_p + pair);
         o_common[pair] = common; o_denom[pair] = denom;

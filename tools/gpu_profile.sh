@@ -15,7 +15,7 @@ echo "ncu list rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:'k1q_|k1_fa|k2_hash' -s 80 -c 8 \
     -o gpurun_out/prof_${tag} -f python bench.py $prof > gpurun_out/ncu_full_${tag}.log 2>&1
 echo "ncu full rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:'rs_|k3' -s 20 -c 16 \
+ncu --set full --clock-control none --import-source on -k regex:'bs_|k3t|k4_|rs_' -s 10 -c 16 \
     -o gpurun_out/prof_sel_${tag} -f python bench.py $prof > gpurun_out/ncu_full_sel_${tag}.log 2>&1
 echo "ncu full sel rc=$?"
 ls -la gpurun_out
