@@ -150,19 +150,29 @@ __global__ void __launch_bounds__(256) bs_hist(const u64 *__restrict__ keys, uin
     if (i < n) atomicAdd(hist + (uint32_t)(keys[i] >> shift), 1u);
 }
 
-// one CTA: exclusive scan of the bucket counts -> start[], cursors zeroed
+// one CTA: exclusive scan of the bucket counts -> start[], cursors zeroed.  Thread t owns buckets [64 t, 64 t + 64)
+// (16-byte accesses; the counts are read twice rather than kept in 64 registers, which would spill at 1,024 threads)
 __global__ void __launch_bounds__(1024) bs_scan(const uint32_t *__restrict__ hist, uint32_t *__restrict__ start,
                                                 uint32_t *__restrict__ cursor) {
     __shared__ uint32_t s_w[33];
     constexpr int PER = BS_BUCKETS / 1024;
     const uint32_t t = threadIdx.x;
-    uint32_t v[PER], mine = 0;
-#pragma unroll
-    for (int i = 0; i < PER; i++) { v[i] = hist[t * PER + i]; mine += v[i]; }
+    const uint4 *h4 = reinterpret_cast<const uint4 *>(hist + (size_t)t * PER);
+    uint32_t mine = 0;
+#pragma unroll 4
+    for (int i = 0; i < PER / 4; i++) { const uint4 v = h4[i]; mine += v.x + v.y + v.z + v.w; }
     uint32_t total;
     uint32_t run = block_excl_sum<1024>(mine, s_w, total);
-#pragma unroll
-    for (int i = 0; i < PER; i++) { start[t * PER + i] = run; cursor[t * PER + i] = 0; run += v[i]; }
+    uint4 *s4 = reinterpret_cast<uint4 *>(start + (size_t)t * PER);
+    uint4 *c4 = reinterpret_cast<uint4 *>(cursor + (size_t)t * PER);
+#pragma unroll 4
+    for (int i = 0; i < PER / 4; i++) {
+        const uint4 v = h4[i];
+        uint4 o;
+        o.x = run; run += v.x; o.y = run; run += v.y; o.z = run; run += v.z; o.w = run; run += v.w;
+        s4[i] = o;
+        c4[i] = make_uint4(0, 0, 0, 0);
+    }
     if (t == 1023) start[BS_BUCKETS] = run;
 }
 
@@ -215,11 +225,11 @@ __global__ void __launch_bounds__(256) bs_fix(const uint32_t *__restrict__ start
     }
 }
 
-// sorts n pairs (keys <= 2^key_bits - 1) from (ka, va) into (kb, vb); hist scratch: 3 * BS_BUCKETS + 1 words
+// sorts n pairs (keys <= 2^key_bits - 1) from (ka, va) into (kb, vb); hist scratch: 3 * BS_BUCKETS + 4 words
 void bucket_sort_pairs(const LaunchCtx &lc, const u64 *ka, const uint32_t *va, u64 *kb, uint32_t *vb, uint32_t n, int key_bits,
                        uint32_t *scratch) {
     const int shift = key_bits > BS_BITS ? key_bits - BS_BITS : 0;
-    uint32_t *hist = scratch, *start = scratch + BS_BUCKETS, *cursor = scratch + 2 * BS_BUCKETS + 1;
+    uint32_t *hist = scratch, *start = scratch + BS_BUCKETS, *cursor = scratch + 2 * BS_BUCKETS + 4;   // 16-byte aligned rows
     cudaMemsetAsync(hist, 0, BS_BUCKETS * sizeof(uint32_t), lc.stream);
     bs_hist<<<div_up(n, 256), 256, 0, lc.stream>>>(ka, n, shift, hist);
     bs_scan<<<1, 1024, 0, lc.stream>>>(hist, start, cursor);
@@ -631,7 +641,7 @@ void launch_table_finish(const LaunchCtx &lc, const SelectBufs &sb, JobDev *jd, 
                          int sketch_size, int all_entries) {
     const u64 *keys;
     const uint32_t *vals;
-    if (n >= 2 && n <= (1u << 20) && (size_t)256 * div_up(sb.cap, RS_TILE) >= (size_t)3 * BS_BUCKETS + 2) {
+    if (n >= 2 && n <= (1u << 20) && (size_t)256 * div_up(sb.cap, RS_TILE) >= (size_t)3 * BS_BUCKETS + 4) {
         // few, evenly spread hash values: bucket sort (4 launches) into the idle ping-pong pair
         bucket_sort_pairs(lc, sb.keys_a, sb.vals_a, sb.keys_b, sb.vals_b, n, key_bits, sb.hist);
         keys = sb.keys_b; vals = sb.vals_b;

@@ -57,7 +57,7 @@ def main():
         refs = eng.load_sketch_set([h for h, _ in refs_sk], [l for _, l in refs_sk], K, S, names=[f"ref{i}" for i in range(24)])
         rng = np.random.Generator(np.random.PCG64(20240100))
         queries = [synth.fasta_bytes(synth.mutate(g0, float(rng.uniform(0, 0.02)), 20240100 + i)) for i in range(args.assemblies)]
-        classify_batch(eng, queries[:2], refs, k=K, s=S)          # warm-up
+        classify_batch(eng, queries, refs, k=K, s=S)              # warm-up (fills the sketch-buffer pool)
         l0 = eng.launch_count()
         t0 = time.perf_counter()
         rows = classify_batch(eng, queries, refs, k=K, s=S)
