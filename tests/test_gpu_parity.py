@@ -652,3 +652,36 @@ def test_bgzf_and_multi_member_inputs_stream_to_the_same_sketch(engine, reads, t
     sk = engine.sketch_reads([p1, p2], k=27, s=50000, m=3)
     assert_same_sketch(sk, ref)
     assert sk.stats.inflate_s > 0 and sk.stats.bytes_in == len(reads[0]) + len(reads[1])
+
+
+def test_merge_counts_exact_for_clustered_keys_and_both_code_paths(engine):
+    """ac_merge_counts (owner merge of the multi-GPU exchange): sums of equal hashes, >= m kept, ascending.
+    Keys crowded into a few sort buckets (shared top bits) exercise the bucket sort's per-bucket heap sort; the
+    all-ones key cannot live in the count table and forces the radix-sort fallback.  Both must be exact."""
+    import torch
+    from auriclass_b200.sharded import CudaTableBackend
+    be = CudaTableBackend(engine)
+    rng = np.random.default_rng(123)
+    for case in ("uniform", "crowded", "all_ones"):
+        if case == "uniform":
+            base = rng.integers(0, 1 << 57, 20_000, dtype=np.uint64)
+        elif case == "crowded":   # 3 clusters of nearby values: thousands of keys per bucket
+            base = np.concatenate([(np.uint64(c) << np.uint64(50)) + rng.integers(0, 1 << 20, 3000, dtype=np.uint64) for c in (1, 7, 40)])
+        else:
+            base = np.concatenate([rng.integers(0, 1 << 63, 5000, dtype=np.uint64), np.array([2**64 - 1] * 3, np.uint64)])
+        keys = np.concatenate([base, base[::2], base[::3], rng.integers(0, 1 << 57, 1000, dtype=np.uint64)])
+        cnts = rng.integers(1, 3, keys.size).astype(np.uint32)
+        perm = rng.permutation(keys.size)
+        keys, cnts = keys[perm], cnts[perm]
+        for m in (1, 3):
+            h = torch.from_numpy(keys.view(np.int64).copy()).cuda()
+            c = torch.from_numpy(cnts.view(np.int32).copy()).cuda()
+            n_q = be.merge_counts(h, c, m)
+            torch.cuda.synchronize()
+            u, inv = np.unique(keys, return_inverse=True)
+            tot = np.bincount(inv, weights=cnts).astype(np.uint64)
+            want_h, want_c = u[tot >= m], tot[tot >= m]
+            assert n_q == want_h.size, (case, m)
+            got_h = h[:n_q].cpu().numpy().view(np.uint64)
+            got_c = c[:n_q].cpu().numpy().view(np.uint32)
+            assert np.array_equal(got_h, want_h) and np.array_equal(got_c.astype(np.uint64), want_c), (case, m)
