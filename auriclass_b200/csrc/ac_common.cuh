@@ -11,7 +11,7 @@ constexpr int K1_THREADS = 256;                      // parser CTA
 constexpr int K1_CHUNK = 32;                         // raw bytes per parser thread (one 32-bit mask)
 constexpr int K1_TILE = K1_THREADS * K1_CHUNK;       // 8 KiB of raw text per parser CTA
 constexpr int Z_CARRY = 32;                          // bytes of the base stream carried between segments (>= k-1)
-constexpr size_t SEG_BYTES = 128u << 20;             // raw text per segment: ~13 waves of K2 CTAs, few dependent launches
+constexpr size_t SEG_BYTES = 256u << 20;             // raw text per segment: few dependent launches (measured: 64 MiB 5.13, 128 MiB 4.85, 256 MiB 4.75, 512 MiB 4.78 ms per C2 isolate)
 constexpr size_t SEG_SAFE_BYTES = 32u << 20;         // segment size when every window may be a candidate (tau = max / safe mode)
 #ifndef AC_K2_THREADS
 #define AC_K2_THREADS 128

@@ -435,12 +435,16 @@ def main() -> None:
         fma_floor_s = n_kmers * (14.0 / pipe["imad_wide"] + 26.0 / pipe["imad"]) if min(pipe.values()) > 0 else 0.0
         alu_floor_s = n_kmers * 44.0 / pipe["lop3"] if pipe["lop3"] > 0 else 0.0
         floor_s = max(fma_floor_s, alu_floor_s)
-        n_seg = -(-nbytes // (int(os.environ.get("AC_SEG_MB", "128")) << 20))  # K2 launches per step = segments (ac_common.cuh SEG_BYTES)
+        n_seg = -(-nbytes // (int(os.environ.get("AC_SEG_MB", "256")) << 20))  # K2 launches per step = segments (ac_common.cuh SEG_BYTES)
         traffic = None
         tp = ROOT / "profiles" / "k2_traffic.json"
         if tp.exists():
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                seg_mb = int(os.environ.get("AC_SEG_MB", "256"))
+                traffic = tj.get("dram_bytes_per_launch")
+                if traffic is not None:   # captured on a `segment_mb` segment: proportional to the bases per launch
+                    traffic = int(traffic * min(seg_mb << 20, nbytes) / (int(tj.get("segment_mb", seg_mb)) << 20))
             except Exception:
                 traffic = None
         out = {
