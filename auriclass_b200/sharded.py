@@ -93,34 +93,18 @@ class CudaTableBackend:
         tau = C.c_uint64()
         spec = C.c_int()
         info = SketchInfo()
-        import time as _t
-        _t0 = _t.perf_counter()
-        _tr = []
         try:
             check(self.lib.ac_sketch_end_local(job, C.byref(n), C.byref(tau), C.byref(spec), C.byref(info)))
-            _tr.append(("end_local", _t.perf_counter()))
             tau_cut = tau_cut_fn(int(tau.value))
-            _tr.append(("tau_cut", _t.perf_counter()))
             begins = (C.c_uint64 * (n_ranges + 1))()
             check(self.lib.ac_job_table_ranges(job, tau_cut, n_ranges, begins))
-            _tr.append(("ranges", _t.perf_counter()))
             b = [int(x) for x in begins]
             n_send = b[n_ranges]
             h = torch.empty(max(n_send, 1), dtype=torch.int64, device=self.device)
             c = torch.empty(max(n_send, 1), dtype=torch.int32, device=self.device)
             check(self.lib.ac_job_table_export(job, 0, n_send, h.data_ptr(), c.data_ptr()))
-            _tr.append(("export", _t.perf_counter()))
         finally:
             self.lib.ac_sketch_abort(job)  # frees the job; the exported copy is ours
-        _tr.append(("abort", _t.perf_counter()))
-        import os as _os
-        if _os.environ.get("AC_TRACE"):
-            prev = _t0
-            out = []
-            for nm, tt in _tr:
-                out.append(f"{nm} {1e3 * (tt - prev):.3f}")
-                prev = tt
-            print("[py trace] " + " | ".join(out), flush=True)
         splits = [b[r + 1] - b[r] for r in range(n_ranges)]
         counters = (info.n_records, info.n_kept, info.total_len, info.n_kmers, info.n_candidates)
         return splits, LocalTable(h[:n_send], c[:n_send], tau_cut, counters)

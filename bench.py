@@ -444,7 +444,7 @@ def main() -> None:
                 seg_mb = int(os.environ.get("AC_SEG_MB", "256"))
                 traffic = tj.get("dram_bytes_per_launch")
                 if traffic is not None:   # captured on a `segment_mb` segment: proportional to the bases per launch
-                    traffic = int(traffic * min(seg_mb << 20, nbytes) / (int(tj.get("segment_mb", seg_mb)) << 20))
+                    traffic = int(traffic * (nbytes / n_seg) / (int(tj.get("segment_mb", seg_mb)) << 20))
             except Exception:
                 traffic = None
         out = {
