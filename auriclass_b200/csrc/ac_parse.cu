@@ -48,30 +48,47 @@ __device__ __forceinline__ uint32_t newline_bits(uint32_t w) {
 }
 
 // Loads the thread's 32 raw bytes (two 16-byte vector loads) and builds per-byte masks.
-__device__ __forceinline__ void load_chunk(const SegDesc &sd, uint32_t tile, uint32_t tid, uint32_t w[8],
-                                           ChunkMasks &m) {
+template <bool WITH_NL>
+__device__ __forceinline__ void load_chunk_t(const SegDesc &sd, uint32_t tile, uint32_t tid, uint32_t w[8],
+                                             ChunkMasks &m) {
     const long long pos = (long long)tile * K1_TILE + (long long)tid * K1_CHUNK;
     const long long lo = sd.skip, hi = (long long)sd.skip + sd.len;
     const long long real_hi = hi - (sd.append_nl ? 1 : 0);
+    const long long tile_lo = (long long)tile * K1_TILE;
+    if (tile_lo >= lo && tile_lo + K1_TILE <= real_hi) {
+        // interior tile (all but the first and last of a segment): every byte is text, no range arithmetic per thread
+        const uint4 *src = reinterpret_cast<const uint4 *>(sd.base + pos);
+        const uint4 x = __ldg(src), y = __ldg(src + 1);
+        w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w; w[4] = y.x; w[5] = y.y; w[6] = y.z; w[7] = y.w;
+        m.valid = 0xffffffffu;
+    } else {
 #pragma unroll
-    for (int v = 0; v < 2; v++) {
-        const long long p = pos + 16 * v;
-        uint4 x = make_uint4(0, 0, 0, 0);
-        if (p < real_hi && p + 16 > lo) x = __ldg(reinterpret_cast<const uint4 *>(sd.base + p));
-        w[4 * v + 0] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+        for (int v = 0; v < 2; v++) {
+            const long long p = pos + 16 * v;
+            uint4 x = make_uint4(0, 0, 0, 0);
+            if (p < real_hi && p + 16 > lo) x = __ldg(reinterpret_cast<const uint4 *>(sd.base + p));
+            w[4 * v + 0] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+        }
+        long long a = (lo > pos ? lo : pos) - pos, b = (hi < pos + 32 ? hi : pos + 32) - pos;
+        m.valid = (b > a) ? bit_range((int)a, (int)b) : 0u;
+        if (sd.append_nl && hi - 1 >= pos && hi - 1 < pos + 32) {
+            const int j = (int)(hi - 1 - pos);
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++)
+                if (jj == (j >> 2)) w[jj] = (w[jj] & ~(0xFFu << (8 * (j & 3)))) | (0x0Au << (8 * (j & 3)));
+        }
     }
-    long long a = (lo > pos ? lo : pos) - pos, b = (hi < pos + 32 ? hi : pos + 32) - pos;
-    m.valid = (b > a) ? bit_range((int)a, (int)b) : 0u;
-    if (sd.append_nl && hi - 1 >= pos && hi - 1 < pos + 32) {
-        const int j = (int)(hi - 1 - pos);
+    if (WITH_NL) {
+        uint32_t nl = 0;
 #pragma unroll
-        for (int jj = 0; jj < 8; jj++)
-            if (jj == (j >> 2)) w[jj] = (w[jj] & ~(0xFFu << (8 * (j & 3)))) | (0x0Au << (8 * (j & 3)));
+        for (int j = 0; j < 8; j++) nl |= (((newline_bits(w[j]) >> 7) * 0x01020408u) >> 24) << (4 * j);
+        m.nl = nl & m.valid;
+    } else {
+        m.nl = 0;   // the caller has the mask from an earlier pass
     }
-    uint32_t nl = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) nl |= (((newline_bits(w[j]) >> 7) * 0x01020408u) >> 24) << (4 * j);
-    m.nl = nl & m.valid;
+}
+__device__ __forceinline__ void load_chunk(const SegDesc &sd, uint32_t tile, uint32_t tid, uint32_t w[8], ChunkMasks &m) {
+    load_chunk_t<true>(sd, tile, tid, w, m);
 }
 
 // Is the byte just before this thread's first valid byte a newline?  (seg_first_ls: value to use
@@ -289,6 +306,8 @@ struct TileArrays {          // passed by value
     uint32_t *nl;            // [cap] newline count            -> (k1q_scan) phase of the line holding the tile's first byte
     uint32_t *c[4];          // [cap] bytes in lines of tile-local index r (mod 4); c[0] -> (k1q_scan) output offset
     uint32_t *flag;          // [1]   bit 31: set by the owner of the segment's last byte, bit 0: that byte is '\n'
+    uint32_t *nlmask;        // [cap * K1_THREADS] newline mask of every 32-byte chunk: k1q_count -> k1q_emit (4 B per 32 B of text
+                             // through L2/HBM instead of recomputing the byte tests)
 };
 
 __global__ void __launch_bounds__(K1_THREADS) k1q_count(SegDesc sd, TileArrays ta) {
@@ -299,6 +318,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1q_count(SegDesc sd, TileArrays t
     uint32_t w[8];
     ChunkMasks m;
     load_chunk(sd, tile, tid, w, m);
+    ta.nlmask[(size_t)tile * K1_THREADS + tid] = m.nl;
     uint32_t total_nl;
     const uint32_t L0 = block_excl_sum<K1_THREADS>(__popc(m.nl), s_w, total_nl);  // syncs: s_acc is zeroed
     const LineMasks lm = line_index_masks(m.nl);
@@ -312,7 +332,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1q_count(SegDesc sd, TileArrays t
         atomicAdd(&s_acc[0], lo & 0xFFFFu); atomicAdd(&s_acc[1], lo >> 16);
         atomicAdd(&s_acc[2], hi & 0xFFFFu); atomicAdd(&s_acc[3], hi >> 16);
     }
-    if (m.valid) {  // the thread that owns the segment's last byte reports whether it is a newline
+    if (tile + 1 == sd.n_tiles && m.valid) {  // (last tile only) the thread that owns the segment's last byte reports whether it is a newline
         const int vhi = 32 - __clz(m.valid);
         const long long pos0 = (long long)tile * K1_TILE + (long long)tid * K1_CHUNK;
         if (pos0 + vhi == (long long)sd.skip + sd.len) *ta.flag = 0x80000000u | ((m.nl >> (vhi - 1)) & 1u);
@@ -406,7 +426,8 @@ __global__ void __launch_bounds__(K1_THREADS) k1q_emit(SegDesc sd, TileArrays ta
     const ParseState ps = jd->ps[sd.serial & 1u];
     uint32_t w[8];
     ChunkMasks m;
-    load_chunk(sd, tile, tid, w, m);
+    load_chunk_t<false>(sd, tile, tid, w, m);
+    m.nl = ta.nlmask[(size_t)tile * K1_THREADS + tid];
 #pragma unroll
     for (int j = 0; j < 8; j++) s_words[tid * SW_STRIDE + j] = w[j];
     uint32_t total_nl;
@@ -577,6 +598,7 @@ void launch_parse_segment(const LaunchCtx &lc, const SegDesc &sd, unsigned long 
         ta.nl = tile_arr;
         for (int q = 0; q < 4; q++) ta.c[q] = tile_arr + (size_t)(q + 1) * tile_cap;
         ta.flag = tile_arr + 5 * tile_cap;
+        ta.nlmask = tile_arr + 5 * tile_cap + 4;
         k1q_count<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, ta);
         k1q_scan<<<1, SCAN_T, 0, lc.stream>>>(sd, ta, jd, Zprev, Z);
         k1q_emit<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, ta, jd, Z);
@@ -589,7 +611,7 @@ void launch_parse_segment(const LaunchCtx &lc, const SegDesc &sd, unsigned long 
 size_t parse_tile_array_words(size_t max_tiles, size_t *tile_cap) {
     const size_t cap = ((max_tiles + SCAN_ROUND - 1) / SCAN_ROUND) * SCAN_ROUND;  // k1q_scan reads whole rounds
     *tile_cap = cap;
-    return 5 * cap + 4;
+    return 5 * cap + 4 + cap * K1_THREADS;   // per-tile numbers, the flag word, one newline mask per 32-byte chunk
 }
 
 }  // namespace ac
