@@ -306,8 +306,9 @@ struct TileArrays {          // passed by value
     uint32_t *nl;            // [cap] newline count            -> (k1q_scan) phase of the line holding the tile's first byte
     uint32_t *c[4];          // [cap] bytes in lines of tile-local index r (mod 4); c[0] -> (k1q_scan) output offset
     uint32_t *flag;          // [1]   bit 31: set by the owner of the segment's last byte, bit 0: that byte is '\n'
-    uint32_t *nlmask;        // [cap * K1_THREADS] newline mask of every 32-byte chunk: k1q_count -> k1q_emit (4 B per 32 B of text
-                             // through L2/HBM instead of recomputing the byte tests)
+    uint2 *nlmask;           // [cap * K1_THREADS] per 32-byte chunk: .x newline mask, .y newlines before the chunk inside its tile;
+                             // k1q_count -> k1q_emit (8 B per 32 B of text through L2/HBM instead of recomputing the byte tests
+                             // and re-running the block scan)
 };
 
 __global__ void __launch_bounds__(K1_THREADS) k1q_count(SegDesc sd, TileArrays ta) {
@@ -318,9 +319,9 @@ __global__ void __launch_bounds__(K1_THREADS) k1q_count(SegDesc sd, TileArrays t
     uint32_t w[8];
     ChunkMasks m;
     load_chunk(sd, tile, tid, w, m);
-    ta.nlmask[(size_t)tile * K1_THREADS + tid] = m.nl;
     uint32_t total_nl;
     const uint32_t L0 = block_excl_sum<K1_THREADS>(__popc(m.nl), s_w, total_nl);  // syncs: s_acc is zeroed
+    ta.nlmask[(size_t)tile * K1_THREADS + tid] = make_uint2(m.nl, L0);
     const LineMasks lm = line_index_masks(m.nl);
     // bytes per tile-local line index: chunk-local index r belongs to tile-local index (r + L0) & 3
     uint32_t cnt[4];
@@ -418,7 +419,6 @@ __global__ void __launch_bounds__(SCAN_T) k1q_scan(SegDesc sd, TileArrays ta, Jo
 
 __global__ void __launch_bounds__(K1_THREADS) k1q_emit(SegDesc sd, TileArrays ta, JobDev *__restrict__ jd, uint8_t *__restrict__ Z) {
     __shared__ uint32_t s_w[33];
-    __shared__ uint32_t s_last[8];
     __shared__ __align__(16) uint32_t s_words[K1_THREADS * SW_STRIDE + 4];
     __shared__ __align__(16) uint8_t s_out[K1_TILE + 32];
     const uint32_t tile = blockIdx.x, tid = threadIdx.x;
@@ -427,12 +427,17 @@ __global__ void __launch_bounds__(K1_THREADS) k1q_emit(SegDesc sd, TileArrays ta
     uint32_t w[8];
     ChunkMasks m;
     load_chunk_t<false>(sd, tile, tid, w, m);
-    m.nl = ta.nlmask[(size_t)tile * K1_THREADS + tid];
+    const size_t chunk = (size_t)tile * K1_THREADS + tid;
+    const uint2 from_count = ta.nlmask[chunk];
+    m.nl = from_count.x;
+    const uint32_t L0 = from_count.y;
 #pragma unroll
     for (int j = 0; j < 8; j++) s_words[tid * SW_STRIDE + j] = w[j];
-    uint32_t total_nl;
-    const uint32_t L0 = block_excl_sum<K1_THREADS>(__popc(m.nl), s_w, total_nl);
-    const bool prev_nl = prev_is_newline(sd, tile, m, ps.at_line_start, s_last);
+    // is the byte before this chunk's first valid byte a newline?  (the previous chunk's mask answers it)
+    uint32_t up = __shfl_up_sync(FULL, m.nl >> 31, 1);
+    if ((tid & 31u) == 0) up = chunk ? (ta.nlmask[chunk - 1].x >> 31) : 0u;
+    // (the segment's first byte sits in chunk 0 at bit sd.skip < 16: there the parser state of the previous segment decides)
+    const bool prev_nl = m.valid ? ((chunk == 0) ? (ps.at_line_start != 0) : (up != 0)) : false;
     const LineMasks lm = line_index_masks(m.nl);
     const uint32_t ph = (tile_phase + L0) & 3u;       // phase of the line holding the chunk's first byte
     const uint32_t emit = lines_of(lm, (1u - ph) & 3u, m.valid);   // sequence lines, newline included (-> separator)
@@ -598,7 +603,7 @@ void launch_parse_segment(const LaunchCtx &lc, const SegDesc &sd, unsigned long 
         ta.nl = tile_arr;
         for (int q = 0; q < 4; q++) ta.c[q] = tile_arr + (size_t)(q + 1) * tile_cap;
         ta.flag = tile_arr + 5 * tile_cap;
-        ta.nlmask = tile_arr + 5 * tile_cap + 4;
+        ta.nlmask = reinterpret_cast<uint2 *>(tile_arr + 5 * tile_cap + 4);   // (8-byte aligned: cap is a multiple of 8192)
         k1q_count<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, ta);
         k1q_scan<<<1, SCAN_T, 0, lc.stream>>>(sd, ta, jd, Zprev, Z);
         k1q_emit<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, ta, jd, Z);
@@ -611,7 +616,7 @@ void launch_parse_segment(const LaunchCtx &lc, const SegDesc &sd, unsigned long 
 size_t parse_tile_array_words(size_t max_tiles, size_t *tile_cap) {
     const size_t cap = ((max_tiles + SCAN_ROUND - 1) / SCAN_ROUND) * SCAN_ROUND;  // k1q_scan reads whole rounds
     *tile_cap = cap;
-    return 5 * cap + 4 + cap * K1_THREADS;   // per-tile numbers, the flag word, one newline mask per 32-byte chunk
+    return 5 * cap + 4 + 2 * cap * K1_THREADS;   // per-tile numbers, the flag word, (mask, count) per 32-byte chunk
 }
 
 }  // namespace ac
