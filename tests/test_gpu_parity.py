@@ -685,3 +685,17 @@ def test_merge_counts_exact_for_clustered_keys_and_both_code_paths(engine):
             got_h = h[:n_q].cpu().numpy().view(np.uint64)
             got_c = c[:n_q].cpu().numpy().view(np.uint32)
             assert np.array_equal(got_h, want_h) and np.array_equal(got_c.astype(np.uint64), want_c), (case, m)
+
+
+@pytest.mark.parametrize("k,m", [(12, 2), (16, 3), (17, 1), (24, 2), (32, 3)])
+def test_speculative_count_table_for_other_k(engine, k, m):
+    """The count-table pass with 32-bit hashes (k <= 16: 27-bit bucket space), the first 64-bit k, and the widest k:
+    ~10 MB of reads is enough for the speculative threshold at s = 1000."""
+    contigs = synth.genome(seed=50 + k, scale=0.02)
+    fq = synth.fastq_reads(contigs, 32_000, seed=60 + k).tobytes()
+    assert len(fq) > (8 << 20)
+    ref = oracle.sketch_parallel([fq], k, 1000, m)
+    sk = engine.sketch_bytes([fq], k=k, s=1000, m=m, chunk=3 << 20)
+    assert_same_sketch(sk, ref)
+    assert sk.info["passes"] == 1 and sk.info["n_candidates"] < sk.info["n_kmers"] // 8
+    assert sk.info["hash_bits"] == (64 if k > 16 else 32)
