@@ -572,7 +572,7 @@ static int run_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_o
     j->bytes_done += seg_len;
     if (j->table) {
         // the threshold follows the histogram of qualified keys: a 5 us kernel, no host round trip.  Early
-        // segments pull tau from the speculative 1/16 down to ~1.3x its final value; later ones barely move it.
+        // segments pull tau from the speculative 1/32 down to ~1.3x its final value; later ones barely move it.
         if (j->seg_serial <= 4 || (j->seg_serial & 3u) == 0) {
             ProfScope ps(c, 2);
             launch_table_tau_update(lc, c->ct, c->d_jd, j->s);
@@ -583,7 +583,7 @@ static int run_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_o
     if (j->safe || j->bytes_done >= j->next_mark) {
         int rc = consolidate(j);
         if (rc) return rc;
-        // one early consolidation pulls tau from the speculative 1/16 down to ~1.3x its final value; after that
+        // one early consolidation pulls tau from the speculative 1/32 down to ~1.3x its final value; after that
         // the candidate stream is a trickle (~0.5 % of the k-mers) that is folded in when the buffer fills
         // (cand_bound guard above) or at the end of the job
         j->next_mark = (size_t)-1;
