@@ -80,6 +80,7 @@ SIGNATURES = {
     "ac_last_job_times": (C.c_int, [_vp, C.POINTER(C.c_float * 4)]),
     "ac_int_peak": (C.c_int, [_vp, _dp]),
     "ac_pipe_rates": (C.c_int, [_vp, C.POINTER(C.c_double * 3)]),
+    "ac_alu_rates": (C.c_int, [_vp, C.POINTER(C.c_double * 5)]),
 }
 
 _lib = None

@@ -386,6 +386,15 @@ extern "C" int ac_pipe_rates(ac_ctx *c, double rates[3]) {
     return AC_OK;
 }
 
+extern "C" int ac_alu_rates(ac_ctx *c, double rates[5]) {
+    if (!c || !rates) return fail(AC_E_PARAM, "ac_alu_rates: NULL argument");
+    CK(cudaSetDevice(c->dev));
+    LaunchCtx lc{c->s_comp, &c->launches};
+    run_alu_rates(lc, rates);
+    CK(cudaGetLastError());
+    return AC_OK;
+}
+
 // ------------------------------------------------------------------ profiling helpers
 struct ProfScope {
     ac_ctx *c; int slot; cudaEvent_t a, b; bool on;

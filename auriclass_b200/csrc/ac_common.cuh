@@ -192,6 +192,7 @@ void launch_dist_pairs(const LaunchCtx &lc, const unsigned long long *a_hashes, 
 
 double run_int_peak(const LaunchCtx &lc);
 void run_pipe_rates(const LaunchCtx &lc, double rates[3]);
+void run_alu_rates(const LaunchCtx &lc, double rates[5]);
 
 
 #if defined(__CUDACC__)

@@ -356,6 +356,31 @@ __global__ void __launch_bounds__(256) k_pipe_rate(unsigned long long *out, int 
     if ((uint32_t)r == 0x12345678u) out[0] = r;  // practically never true; keeps the chains alive
 }
 
+// ---- alu-pipe issue rates by instruction kind: 0 SHF (funnel shift), 1 PRMT, 2 IADD3, 3 ISETP + SEL pairs,
+// 4 LEA (shift-and-add).  K2's loop is half SHF/LOP3/IADD3/SEL/PRMT; the roofline needs to know whether they all
+// issue at the LOP3 rate.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_alu_rate(unsigned long long *out, int iters) {
+    uint32_t a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = threadIdx.x * 0x9E3779B1u + blockIdx.x + i;
+    const uint32_t m = 0x9E3779B1u + threadIdx.x, m2 = 0x7F4A7C15u ^ blockIdx.x;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (MODE == 0) asm volatile("shf.l.wrap.b32 %0, %0, %1, 13;" : "+r"(a[i]) : "r"(m));
+            else if (MODE == 1) asm volatile("prmt.b32 %0, %0, %1, 0x2503;" : "+r"(a[i]) : "r"(m));
+            else if (MODE == 2) asm volatile("{\n.reg .u32 t;\nadd.cc.u32 t, %0, %1;\naddc.u32 %0, %0, %1;\n}" : "+r"(a[i]) : "r"(m));
+            else if (MODE == 3) asm volatile("{\n.reg .pred p;\nsetp.lt.u32 p, %0, %1;\nselp.b32 %0, %2, %0, p;\n}" : "+r"(a[i]) : "r"(m), "r"(m2));
+            else asm volatile("{\n.reg .u32 t;\nshl.b32 t, %0, 2;\nadd.u32 %0, t, %1;\n}" : "+r"(a[i]) : "r"(m));
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r ^= a[i];
+    if (r == 0x12345678u) out[0] = r;  // practically never true; keeps the chains alive
+}
+
 }  // namespace
 
 void launch_dist(const LaunchCtx &lc, const unsigned long long *ref_hashes, const unsigned long long *ref_off,
@@ -434,6 +459,44 @@ static double pipe_rate_one(const LaunchCtx &lc, unsigned long long *d, int sms)
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return best;
+}
+
+template <int MODE>
+static double alu_rate_one(const LaunchCtx &lc, unsigned long long *d, int sms, double instr_per_step) {
+    const int iters = 4096, blocks = sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0, lc.stream);
+        k_alu_rate<MODE><<<blocks, threads, 0, lc.stream>>>(d, iters);
+        cudaEventRecord(e1, lc.stream);
+        cudaEventSynchronize(e1);
+        ++*lc.launches;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double instr = (double)blocks * threads * (double)iters * 8.0 * instr_per_step;
+        if (rep > 0 && ms > 0) best = fmax(best, instr / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return best;
+}
+
+// thread-instructions per second of the alu-pipe instruction kinds of K2, each issued alone:
+// [0] SHF (funnel shift), [1] PRMT, [2] IADD3 (carry pair), [3] ISETP + SEL pairs, [4] LEA
+void run_alu_rates(const LaunchCtx &lc, double rates[5]) {
+    for (int i = 0; i < 5; i++) rates[i] = 0.0;
+    unsigned long long *d = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess) return;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    rates[0] = alu_rate_one<0>(lc, d, sms, 1.0);
+    rates[1] = alu_rate_one<1>(lc, d, sms, 1.0);
+    rates[2] = alu_rate_one<2>(lc, d, sms, 2.0);
+    rates[3] = alu_rate_one<3>(lc, d, sms, 2.0);
+    rates[4] = alu_rate_one<4>(lc, d, sms, 1.0);
+    cudaFree(d);
 }
 
 // thread-instructions per second of IMAD, IMAD.WIDE.U32 and LOP3 issued alone (the pipes K2 lives on)

@@ -5,22 +5,23 @@
 // MinHashHeap::tryInsert (SURVEY.md section 2.2 stages S3-S4, App. A.3/A.4) that run
 // inside `mash sketch` (auriclass/classes.py:576-596, :696-713).
 //
-// One CTA owns K2_TILE consecutive window starts.  The tile (+64 bytes of halo) is
-// brought into shared memory by one TMA bulk copy (cp.async.bulk + mbarrier); the
-// CTA then builds, once, the reverse complement of the whole tile, per-32-byte
-// validity / separator bitmaps, the bitmap of valid window starts, and from it the
-// list of *groups*: every maximal run of valid windows is cut into pieces of 32, so
-// lanes are only spent where there is a k-mer to hash (97 % of the slots for 150 bp
-// reads instead of 82 % with a fixed assignment; gaps of any length cost nothing).
-// A quad of lanes takes a group: lane c hashes windows g+c, g+c+4, ... (stride 4 bytes),
-// so one byte alignment of the 15 words it loads per strand (funnel shifts) makes
-// every key word of its 8 windows a whole register -- no per-window byte slicing, no
-// rolling state, no 2-bit <-> ASCII expansion.  The unrolled 8-window body stays in
-// the instruction cache.
-// Integer-issue bound: ~46 IMAD + ~46 LOP3/SHF/IADD3 per k-mer for the hash alone,
-// ~1 byte of HBM/L2 read per k-mer.
-// Hashes <= tau (device-resident, monotonically shrinking) are staged in shared
-// memory and appended to the candidate buffer with one atomic per CTA.
+// Every warp owns K2_WT consecutive window starts (a CTA is K2_WARPS such warps and one barrier).  The warp's
+// sub-tile (+64 bytes of halo) is brought into shared memory by one TMA bulk copy (cp.async.bulk + mbarrier); the
+// warp then builds, once, the reverse complement of the sub-tile, per-32-byte validity / separator bitmaps, the
+// bitmap of valid window starts, and from it the list of *groups*: every maximal run of valid windows is cut into
+// pieces of 32, so lanes are only spent where there is a k-mer to hash (97 % of the slots for 150 bp reads instead
+// of 82 % with a fixed assignment; gaps of any length cost nothing).
+// A quad of lanes takes a group: lane c hashes windows g+c, g+c+4, ... (stride 4 bytes), so one byte alignment of
+// the 15 words it loads per strand (funnel shifts) makes every key word of its 8 windows a whole register -- no
+// per-window byte slicing, no rolling state, no 2-bit <-> ASCII expansion.
+// Count-table passes (tau <= 1/32 of the hash space) run the FLAT loop: the 8 windows of a lane are one basic block
+// (strand from the first four bases, threshold gate on the high words of the two last fmix products); the ~1 window
+// in 120 that ties or passes the gate is parked in the warp's redo list and hashed again, exactly, by all lanes
+// together when the sub-tile is done.  Passes that start at tau = max keep the branchy loop.
+// Integer-issue bound: 14 IMAD.WIDE + 31 IMAD/IMAD.X and ~47 SHF/LOP3/IADD3/SEL/ISETP per k-mer, both integer pipes
+// ~72 % busy; ~1 byte of HBM/L2 read per k-mer.
+// Hashes <= tau (device-resident, monotonically shrinking) are staged in shared memory and inserted into the count
+// table (or appended to the candidate buffer) by the warp when its sub-tile is done.
 #include "ac_common.cuh"
 #include "kmer_core.cuh"
 
@@ -29,6 +30,9 @@ namespace ac {
 namespace {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+constexpr int K2_REDO = 128;                    // flagged windows a warp parks per sub-tile (flat hot loop)
+constexpr int K2_TB = K2_WT + 64;               // sub-tile bytes staged per warp (window halo + statistics look-back)
 
 // Where candidates go.  Lives in shared memory so that the hot loop carries no kernel parameters
 // (ptxas otherwise hoists their constant-bank loads in front of every window's threshold branch).
@@ -41,7 +45,9 @@ struct SinkShared {
     JobDev *jd;
     CountTable ct;                         // ct.mask != 0: candidates go into the count table
     uint32_t cnt;                          // staged candidates of this CTA (may exceed K2_STAGE: the excess went to global)
+    uint32_t n_redo;                       // flagged windows of the sub-tile (flat hot loop); may exceed K2_REDO: the excess was redone on the spot
     unsigned long long buf[K2_STAGE];
+    uint16_t redo[K2_REDO];                // their start bytes inside the sub-tile
 };
 
 // staging full (tau close to max): opportunistic warp-aggregated append straight to the candidate buffer
@@ -70,16 +76,27 @@ __device__ __noinline__ void cand_stage(uint64_t p1, uint64_t p2, uint32_t windo
     else cand_append_global(h, ss);
 }
 
+// Flat hot loop: a flagged window (first four bases of the two strands tie, or the gate value passes) is hashed
+// again from the sub-tile in shared memory, exactly, and staged if it is a candidate.
+template <int K>
+__device__ __noinline__ void redo_window(const uint32_t *fwd_w, const uint32_t *rc_w, uint32_t p, uint32_t rc_top,
+                                         uint32_t seed, SinkShared *ss) {
+    const unsigned long long h = ackmer::rehash_window<K>(fwd_w, rc_w, p, rc_top - p, seed);
+    if (h > ss->tau) return;
+    uint32_t idx;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(idx) : "r"(smem_u32(&ss->cnt)) : "memory");
+    if (idx < (uint32_t)K2_STAGE) ss->buf[idx] = h;
+    else cand_append_global(h, ss);
+}
+
 template <bool USE64>
 struct CandSink {
-    uint32_t gate;   // 64-bit hashes: high word of tau, + 1 (saturating); 32-bit hashes: tau
+    uint32_t gate;   // ackmer::gate_of_tau
     SinkShared *ss;
     __device__ __forceinline__ void operator()(uint32_t vbits, uint32_t bit, uint64_t p1, uint64_t p2) {
-        // Reject on the high words alone: hi(h) = hi(p1) + hi(p2) + carry, carry in {0, 1}, so
-        // hi(h) <= hi(tau) implies t <= hi(tau) or t == 2^32 - 1 for t = hi(p1) + hi(p2), i.e. t + 1 <= gate (mod 2^32).
-        bool maybe;
-        if constexpr (USE64) maybe = (uint32_t)(p1 >> 32) + (uint32_t)(p2 >> 32) + 1u <= gate;
-        else maybe = ((uint32_t)p1 ^ (uint32_t)(p1 >> 33)) + ((uint32_t)p2 ^ (uint32_t)(p2 >> 33)) <= gate;
+        // p1, p2: half-open fmix values (kmer_core.cuh).  64-bit hashes are rejected on the high word of the digest
+        // alone (gate_value); cand_stage finishes the hash and tests exactly.
+        const bool maybe = ackmer::gate_value<USE64>(p1, p2) <= gate;
         if (maybe) cand_stage<USE64>(p1, p2, vbits & bit, ss);
     }
 };
@@ -102,7 +119,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!ok);
 }
 
-constexpr int K2_TB = K2_WT + 64;               // sub-tile bytes staged per warp (window halo + statistics look-back)
 constexpr int K2_NWV = K2_WT / 32;              // words of a warp's valid-window bitmap
 constexpr int K2_ROUNDS = K2_NWV / 32;          // a lane owns word (32 r + lane) in round r
 // group list capacity: two runs are at least K invalid windows apart, a run of L windows makes ceil(L/32) groups
@@ -130,7 +146,11 @@ __device__ __forceinline__ uint32_t warp_incl_sum(uint32_t v, uint32_t lane) {
 // __syncwarp only.  The prologue / epilogue of one warp (latency bound) thus overlaps the hash loops of the other
 // warps on its sub-partition instead of idling whole CTAs at barriers: with CTA-wide phases only ~64 % of the time
 // enough warps were inside the loop to keep the fmaheavy pipe busy.
-template <int K>
+// FLAT: the hot loop is one basic block per 8 windows (process_quad_windows_flat); flagged windows are parked in the
+// warp's redo list and worked off, all lanes busy, when the sub-tile is done.  Used for count-table passes (tau <=
+// 1/32 of the hash space: ~1 window in 120 is flagged); passes that start at tau = max keep the branchy loop, whose
+// rare path is taken by every window there.
+template <int K, bool FLAT>
 __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t *__restrict__ Z, JobDev *__restrict__ jd,
                                                          unsigned long long *__restrict__ cand,
                                                          unsigned long long cand_cap, uint32_t seed, int ps_slot,
@@ -168,7 +188,7 @@ __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t 
         uint64_t *s_bar = &s_bar_all[warp];
         if (lane == 0) {
             s_wv[K2_NWV] = 0;
-            s_sink.cnt = 0; s_sink.tau = jd->tau;
+            s_sink.cnt = 0; s_sink.n_redo = 0; s_sink.tau = jd->tau;
             s_sink.cand = cand; s_sink.cand_count = &jd->cand_count; s_sink.cand_cap = cand_cap;
             s_sink.overflow = &jd->overflow; s_sink.jd = jd; s_sink.ct = ct;
             mbar_init(s_bar, 1);
@@ -247,12 +267,8 @@ __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t 
         if (n_groups > (uint32_t)K2_MAXG) __trap();  // cannot happen (see K2MaxGroups)
 
         CandSink<(K > 16)> sink;
-        {
-            const unsigned long long tau = s_sink.tau;
-            const uint32_t top = (uint32_t)(tau >> 32);
-            sink.gate = (K > 16) ? (top == 0xffffffffu ? top : top + 1u) : (uint32_t)tau;
-            sink.ss = &s_sink;
-        }
+        sink.gate = ackmer::gate_of_tau(s_sink.tau, K > 16);
+        sink.ss = &s_sink;
         const ackmer::MurmurConsts mc;   // (registers are too scarce to hide these from ptxas' constant folding: 64/thread)
 
         // ---- hash: a quad per group, lane c takes windows g+c+4j
@@ -276,7 +292,27 @@ __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t 
 #pragma unroll
                 for (int i = 0; i < Q::NL; i++) in[i] = rc_w[(QL >> 2) + i];
                 ackmer::preshift<Q::NS>(in, QL & 3u, rw);
-                ackmer::process_quad_windows<K, 0>(fw, rw, vb, seed, mc, sink);
+                if constexpr (FLAT) {
+                    uint32_t flags = 0;
+                    ackmer::process_quad_windows_flat<K, 0, (K > 16)>(fw, rw, seed, mc, sink.gate, flags);
+                    flags &= vb;                     // bit 4j: the lane's window j (byte A + 4j) is valid and flagged
+                    while (flags) {                  // ~2 lanes of the warp per pass
+                        const uint32_t pos = A + (uint32_t)(__ffs(flags) - 1);
+                        flags &= flags - 1u;
+                        uint32_t idx;
+                        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(idx) : "r"(smem_u32(&s_sink.n_redo)) : "memory");
+                        if (idx < (uint32_t)K2_REDO) s_sink.redo[idx] = (uint16_t)pos;
+                        else redo_window<K>(fwd_w, rc_w, pos, (uint32_t)(K2_TB - K), seed, &s_sink);
+                    }
+                } else {
+                    ackmer::process_quad_windows<K, 0>(fw, rw, vb, seed, mc, sink);
+                }
+            }
+            if constexpr (FLAT) {
+                __syncwarp();
+                const uint32_t n_redo = min(s_sink.n_redo, (uint32_t)K2_REDO);
+                for (uint32_t i = lane; i < n_redo; i += 32)
+                    redo_window<K>(fwd_w, rc_w, s_sink.redo[i], (uint32_t)(K2_TB - K), seed, &s_sink);
             }
         }
 
@@ -351,8 +387,13 @@ __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t 
 template <int K>
 void launch_k(const LaunchCtx &lc, const uint8_t *Z, uint32_t max_zbuf, int ps_slot, JobDev *jd, unsigned long long *cand,
               unsigned long long cand_cap, uint32_t seed, const CountTable &ct) {
-    const unsigned grid = div_up(max_zbuf, K2_TILE);
-    k2_hash<K><<<grid, K2_THREADS, 0, lc.stream>>>(Z, jd, cand, cand_cap, seed, ps_slot, ct);
+    const unsigned grid = div_up(max_zbuf, K2_TILE);   // CTAs past the end of the stream leave at once (measured: no cost)
+#if defined(AC_K2_BRANCHY)   // comparison builds: the branchy loop everywhere
+    k2_hash<K, false><<<grid, K2_THREADS, 0, lc.stream>>>(Z, jd, cand, cand_cap, seed, ps_slot, ct);
+#else
+    if (ct.mask) k2_hash<K, true><<<grid, K2_THREADS, 0, lc.stream>>>(Z, jd, cand, cand_cap, seed, ps_slot, ct);
+    else k2_hash<K, false><<<grid, K2_THREADS, 0, lc.stream>>>(Z, jd, cand, cand_cap, seed, ps_slot, ct);
+#endif
     ++*lc.launches;
 }
 

@@ -94,8 +94,8 @@ AC_HD uint32_t key_word(const uint32_t *w) {
     if constexpr (J < (K + 3) / 4) return w[J]; else return 0u;
 }
 
-// h * 5 + c (mod 2^64) with c held in a register pair by the caller: IMAD.WIDE + IMAD on the device
-// (nvcc's own expansion materialises c with two moves and adds the high product separately)
+// h * 5 + c (mod 2^64): IMAD.WIDE + IMAD on the device.  (The shift-and-add form on the alu pipe -- LEA, SHF, two
+// carry adds -- takes 16 cycles off the fmaheavy pipe per window and made K2 3 % slower: the alu pipe is as full.)
 AC_HD uint64_t mul5_add(uint64_t h, uint64_t c) {
 #if defined(__CUDA_ARCH__)
     const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
@@ -116,19 +116,20 @@ struct MurmurConsts {
     AC_HD MurmurConsts() : a(0x52dce729ULL), b(0x38495ab5ULL) {}
 };
 
-// fmix64 without its last `x ^= x >> 33`: that step only changes the low word
-AC_HD uint64_t fmix64_open(uint64_t x) {
-    x ^= x >> 33; x = mul64(x, 0xff51afd7ed558ccdULL);
-    x ^= x >> 33; x = mul64(x, 0xc4ceb9fe1a85ec53ULL);
+// fmix64 up to, not including, its second multiply ("half-open"): q with fmix64(x) = f(q * FMIX_C2), f(p) = p ^ (p >> 33)
+constexpr uint64_t FMIX_C1 = 0xff51afd7ed558ccdULL, FMIX_C2 = 0xc4ceb9fe1a85ec53ULL;
+AC_HD uint64_t fmix64_half(uint64_t x) {
+    x ^= x >> 33; x = mul64(x, FMIX_C1);
+    x ^= x >> 33;
     return x;
 }
-// h1 of the digest from the two open fmix products: fmix(h1) + fmix(h2)
-AC_HD uint64_t murmur3_close(uint64_t p1, uint64_t p2) {
+// h1 of the digest from the two half-open fmix values: fmix(h1) + fmix(h2)
+AC_HD uint64_t murmur3_close(uint64_t q1, uint64_t q2) {
+    const uint64_t p1 = mul64(q1, FMIX_C2), p2 = mul64(q2, FMIX_C2);
     return (p1 ^ (p1 >> 33)) + (p2 ^ (p2 >> 33));
 }
-
-// MurmurHash3_x64_128(key, K, seed) up to the open fmix products (p1, p2); h1 of the digest =
-// murmur3_close(p1, p2).  w[] = the K key bytes as (K+3)/4 little-endian words, bytes past K in the
+// MurmurHash3_x64_128(key, K, seed) up to the half-open fmix values (q1, q2); h1 of the digest =
+// murmur3_close(q1, q2).  w[] = the K key bytes as (K+3)/4 little-endian words, bytes past K in the
 // last word MUST be zero.  Mash: hash = first 8 bytes of the 128-bit digest = h1.
 template <int K>
 AC_HD void murmur3_open(const uint32_t *w, uint32_t seed, const MurmurConsts &mc, uint64_t &p1, uint64_t &p2) {
@@ -162,7 +163,7 @@ AC_HD void murmur3_open(const uint32_t *w, uint32_t seed, const MurmurConsts &mc
     }
     h1 ^= (uint64_t)K; h2 ^= (uint64_t)K;
     h1 += h2; h2 += h1;
-    p1 = fmix64_open(h1); p2 = fmix64_open(h2);
+    p1 = fmix64_half(h1); p2 = fmix64_half(h2);
 }
 
 // h1 of MurmurHash3_x64_128(key, K, seed)
@@ -345,8 +346,8 @@ AC_HD void preshift(const uint32_t *in, uint32_t off, uint32_t *out) {
 
 // fw / rw: the lane's pre-shifted forward / reverse-complement words (QuadCfg::NS each).
 // vbits: bit 4j set = the lane's window j may be emitted.  emit(vbits, 1 << 4j, p1, p2) is called for every
-// window with the open fmix products: the hash is murmur3_close(p1, p2), which the caller only needs to
-// finish for the few windows whose high words can still pass its threshold.
+// window with the half-open fmix values: the hash is murmur3_close(p1, p2), which the caller only needs to
+// finish for the few windows whose gate value (gate_value) can still pass its threshold.
 template <int K, int J, class Emit>
 AC_HD void process_quad_windows(const uint32_t *fw, const uint32_t *rw, uint32_t vbits, uint32_t seed,
                                 const MurmurConsts &mc, Emit &emit) {
@@ -381,6 +382,86 @@ AC_HD void process_quad_windows(const uint32_t *fw, const uint32_t *rw, uint32_t
         emit(vbits, 1u << (4 * J), p1, p2);
         process_quad_windows<K, J + 1, Emit>(fw, rw, vbits, seed, mc, emit);
     }
+}
+
+// ---- branch-free form of the quad pass (K2's hot loop) + the exact per-window re-hash behind it.
+// The value a threshold test compares with gate_of_tau(tau).  64-bit hashes are tested on the high word of the digest
+// alone: h = f(P1) + f(P2) with P = q * FMIX_C2 and f(p) = p ^ (p >> 33) touching only the low word, so
+// hi(h) = hi(P1) + hi(P2) + carry, carry in {0, 1}, and hi(h) <= hi(tau) implies t <= hi(tau) or t == 2^32 - 1 for
+// t = hi(P1) + hi(P2), i.e. t + 1 <= hi(tau) + 1 (mod 2^32).  32-bit hashes (k <= 16): the hash itself against tau.
+// (One product instead of two -- hi((q1 + q2) * FMIX_C2) is t or t + 1 by distributivity -- saves 8 fmaheavy
+// cycles per window and did not change K2's time; the two-product form is kept.)
+template <bool USE64>
+AC_HD uint32_t gate_value(uint64_t q1, uint64_t q2) {
+    const uint64_t p1 = mul64(q1, FMIX_C2), p2 = mul64(q2, FMIX_C2);
+    if constexpr (USE64) return (uint32_t)(p1 >> 32) + (uint32_t)(p2 >> 32) + 1u;
+    else return ((uint32_t)p1 ^ (uint32_t)(p1 >> 33)) + ((uint32_t)p2 ^ (uint32_t)(p2 >> 33));
+}
+AC_HD uint32_t gate_of_tau(uint64_t tau, bool use64) {
+    const uint32_t top = (uint32_t)(tau >> 32);
+    if (!use64) return (uint32_t)tau;
+    return top == 0xffffffffu ? top : top + 1u;
+}
+
+// Same windows as process_quad_windows, as ONE basic block: no branch, no call.  The strand is chosen from the
+// first four bases (cb < fb); a window is *flagged* (bit 4j of flags) when those four bases tie (1 in 256: the
+// choice may be wrong) or when its gate value passes `gate` (it may be a candidate).  Flagged windows are hashed
+// again, exactly, by rehash_window; for all others the only fact needed -- hash > tau -- is already established.
+// The caller masks flags with the window validity bits.
+template <int K, int J, bool USE64>
+AC_HD void process_quad_windows_flat(const uint32_t *fw, const uint32_t *rw, uint32_t seed, const MurmurConsts &mc,
+                                     uint32_t gate, uint32_t &flags) {
+    using C = QuadCfg<K>;
+    if constexpr (J < C::G) {
+        uint32_t f[C::NW], c[C::NW];
+#pragma unroll
+        for (int m = 0; m < C::NW; m++) { f[m] = fw[J + m]; c[m] = rw[C::G - 1 - J + m]; }
+        constexpr uint32_t last_mask = (K & 3) ? ((1u << (8 * (K & 3))) - 1u) : 0xffffffffu;
+        bool use_rc;
+        uint32_t fb = 0, cb = 1;      // compared big-endian first words; equal = the first four bases tie
+        if constexpr (C::NW == 1) {   // the whole k-mer is in the compared word: equal words = equal keys, nothing to redo
+            use_rc = byte_perm(c[0] & last_mask, 0, 0x0123) < byte_perm(f[0] & last_mask, 0, 0x0123);
+        } else {
+            fb = byte_perm(f[0], 0, 0x0123); cb = byte_perm(c[0], 0, 0x0123);
+            use_rc = cb < fb;
+        }
+        uint32_t key[C::NW];
+#pragma unroll
+        for (int m = 0; m < C::NW; m++) key[m] = use_rc ? c[m] : f[m];
+        key[C::NW - 1] &= last_mask;
+        uint64_t q1, q2;
+        murmur3_open<K>(key, seed, mc, q1, q2);
+        const uint32_t gv = gate_value<USE64>(q1, q2);
+#if defined(__CUDA_ARCH__)
+        // opaque to the compiler on purpose: as C++ the tie test turns into a branch around the gate arithmetic
+        asm("{\n.reg .pred t, g;\nsetp.eq.u32 t, %1, %2;\nsetp.le.u32 g, %3, %4;\nor.pred t, t, g;\n@t or.b32 %0, %0, %5;\n}"
+            : "+r"(flags) : "r"(fb), "r"(cb), "r"(gv), "r"(gate), "n"(1u << (4 * J)));
+#else
+        if (fb == cb || gv <= gate) flags |= 1u << (4 * J);
+#endif
+        process_quad_windows_flat<K, J + 1, USE64>(fw, rw, seed, mc, gate, flags);
+    }
+}
+
+// Exact canonical hash of the window that starts at byte p of a byte string held as little-endian words fwd_w[],
+// its reverse complement starting at byte q of rc_w[] (any alignment; reads words (p >> 2) .. (p >> 2) + NW).
+template <int K>
+AC_HD uint64_t rehash_window(const uint32_t *fwd_w, const uint32_t *rc_w, uint32_t p, uint32_t q, uint32_t seed) {
+    constexpr int NW = (K + 3) / 4;
+    constexpr uint32_t last_mask = (K & 3) ? ((1u << (8 * (K & 3))) - 1u) : 0xffffffffu;
+    uint32_t f[NW], c[NW];
+#pragma unroll
+    for (int m = 0; m < NW; m++) {
+        f[m] = funnel_r(fwd_w[(p >> 2) + m], fwd_w[(p >> 2) + m + 1], 8u * (p & 3u));
+        c[m] = funnel_r(rc_w[(q >> 2) + m], rc_w[(q >> 2) + m + 1], 8u * (q & 3u));
+    }
+    f[NW - 1] &= last_mask; c[NW - 1] &= last_mask;
+    const bool use_rc = rc_is_smaller<NW>(f, c);
+    uint32_t key[NW];
+#pragma unroll
+    for (int m = 0; m < NW; m++) key[m] = use_rc ? c[m] : f[m];
+    const uint64_t h = murmur3_h1<K>(key, seed);
+    return K > 16 ? h : (h & 0xffffffffULL);   // Mash: 32-bit hashes for k <= 16
 }
 
 // K1's per-byte sanitiser (scalar form; the kernel uses it per byte of a word).

@@ -194,6 +194,11 @@ class MashGPU:
         check(self.lib.ac_pipe_rates(self.ctx, C.byref(arr)))
         return {"imad": arr[0], "imad_wide": arr[1], "lop3": arr[2]}
 
+    def alu_rates(self) -> dict:
+        arr = (C.c_double * 5)()
+        check(self.lib.ac_alu_rates(self.ctx, C.byref(arr)))
+        return {"shf": arr[0], "prmt": arr[1], "iadd3": arr[2], "isetp_sel": arr[3], "lea": arr[4]}
+
     def _staging(self) -> List[Tuple[int, memoryview]]:
         if not self._pinned:
             for _ in range(2):

@@ -474,7 +474,7 @@ def main() -> None:
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": k2_bytes / hash_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": k2_bytes / hash_s / 1e9 / hbm_peak, "traffic": traffic,
-                         "kernel": "k2_hash<27>", "launches_per_step": int(n_seg), "avg_launch_ms": prof["hash_ms"] / n_seg,
+                         "kernel": "k2_hash<27, FLAT>", "launches_per_step": int(n_seg), "avg_launch_ms": prof["hash_ms"] / n_seg,
                          "algorithmic_bytes_per_launch": k2_bytes / n_seg, "peak_source": peak_src,
                          "note": "K2 is integer-issue bound, not HBM bound: see roofline_int"},
             "roofline_int": {"bound": "int32-issue", "achieved": n_kmers * I_ALG / hash_s / 1e12, "peak": int_peak / 1e12,

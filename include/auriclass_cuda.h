@@ -191,6 +191,10 @@ int ac_int_peak(ac_ctx *ctx, double *instr_per_s);
  * pipe).  bench.py turns them into the pipe-cycle roofline of the hash kernel. */
 int ac_pipe_rates(ac_ctx *ctx, double rates[3]);
 
+/* Issue rates of the alu-pipe instruction kinds of kernel K2, each issued alone in independent chains:
+ * [0] SHF (funnel shift), [1] PRMT, [2] IADD3 (carry pairs), [3] ISETP + SEL pairs, [4] LEA. */
+int ac_alu_rates(ac_ctx *ctx, double rates[5]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -699,3 +699,22 @@ def test_speculative_count_table_for_other_k(engine, k, m):
     assert_same_sketch(sk, ref)
     assert sk.info["passes"] == 1 and sk.info["n_candidates"] < sk.info["n_kmers"] // 8
     assert sk.info["hash_bits"] == (64 if k > 16 else 32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [28, 27, 16])
+def test_flat_loop_redo_list_overflow(engine, k):
+    """K2's flat loop parks windows whose strands tie on the first four bases in a 128-entry list per 2,048 windows.
+    (AT)n reads tie on EVERY window for even k ((AATT)n on every other one), so whole sub-tiles overflow the list
+    and the excess is re-hashed on the spot; the sketch must not notice.  Count-table pass, ~10 MB of reads."""
+    contigs = synth.genome(seed=70 + k, scale=0.02)
+    fq = synth.fastq_reads(contigs, 32_000, seed=80 + k).tobytes()
+    ties = b"".join(b"@t%d\n%s\n+\n%s\n" % (i, (u * 80)[:150], b"I" * 150)
+                    for i in range(4000) for u in (b"AT", b"AATT", b"ACGT"))
+    cut = fq.rfind(b"\n@SYN", 0, len(fq) // 2) + 1
+    buf = fq[:cut] + ties + fq[cut:]
+    assert len(buf) > (8 << 20)
+    ref = oracle.sketch_parallel([buf], k, 1000, 2)
+    sk = engine.sketch_bytes([buf], k=k, s=1000, m=2, chunk=3 << 20)
+    assert_same_sketch(sk, ref)
+    assert sk.info["passes"] == 1

@@ -47,6 +47,36 @@ def _core_hashes(L, seq: bytes, k: int, quad: bool = False) -> np.ndarray:
     return out if k > 16 else out & np.uint64(0xFFFFFFFF)
 
 
+@pytest.mark.parametrize("k", [1, 3, 4, 5, 8, 11, 15, 16, 17, 21, 24, 27, 28, 31, 32])
+def test_k2_flat_loop_keeps_every_hash_below_tau(hostcheck, k):
+    """The flat hot loop (strand from the first four bases, flag on a tie or a passing gate, exact re-hash of the
+    flagged windows) must deliver exactly the hashes <= tau, for thresholds from 1/32 of the space down to 0."""
+    hostcheck.hc_hash_stream_flat.restype = C.c_long
+    hostcheck.hc_hash_stream_flat.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p]
+    rng = np.random.default_rng(100 + k)
+    seq = bytearray(rng.choice(np.frombuffer(b"ACGT", np.uint8), 20_000).tobytes())
+    # palindromic stretches (first four bases of both strands tie), Ns, a low-complexity run
+    seq[500:540] = b"ACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT"
+    seq[3000:3003] = b"NNN"
+    seq[7000:7100] = b"AT" * 50
+    seq[12000:12064] = b"AATT" * 16
+    seq = bytes(seq)
+    a = np.frombuffer(seq, np.uint8).copy()
+    z = np.zeros_like(a)
+    hostcheck.hc_sanitise(a.ctypes.data, a.size, z.ctypes.data)
+    want_all = oracle.all_hashes(b">x\n" + seq + b"\n", k)
+    space = 64 if k > 16 else 32
+    for tau in ((1 << space) // 32, (1 << space) // 250, (1 << space) - 1, 0):
+        out = np.zeros(a.size, np.uint64)
+        n_flagged = C.c_long(0)
+        n = hostcheck.hc_hash_stream_flat(z.ctypes.data, z.size, k, tau, out.ctypes.data, out.size, C.byref(n_flagged))
+        want = want_all[want_all <= np.uint64(tau)]
+        assert n == want.size, (k, tau)
+        assert np.array_equal(out[:n], want), (k, tau)
+        if k >= 12 and tau == (1 << space) // 250:   # the filter is tight: candidates + first-word ties + a few
+            assert n_flagged.value <= n + a.size // 256 * 2 + 400
+
+
 @pytest.mark.parametrize("k", list(range(1, 33)))
 def test_device_hash_core_matches_oracle_all_k(hostcheck, k):
     fa = oracle.read_maybe_gz(D + "NC_001416.1.fasta.gz")
