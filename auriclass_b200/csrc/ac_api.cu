@@ -104,6 +104,11 @@ struct ac_ctx {
     std::vector<SketchBuf> sk_pool;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[3];
     cudaEvent_t ev_job0, ev_job1;
+    // FASTQ look-ahead: k1q_count + k1q_scan of the next segment run on s_aux beside the hash kernel of this one
+    cudaStream_t s_aux;
+    cudaEvent_t ev_emit;       // on s_comp: the last k1q_emit (or the start of the pass) is done -> the tile arrays are free
+    cudaEvent_t ev_pre;        // on s_aux: the pre-launched count + scan are done
+    bool lookahead;            // AC_LOOKAHEAD=1 turns it on
 };
 
 struct ac_job {
@@ -126,6 +131,9 @@ struct ac_job {
     size_t proc_piece, proc_off;      // first unprocessed byte
     size_t pending;                   // fed but unprocessed bytes
     bool first_of_stream;
+    bool pre_valid;                   // count + scan of the next segment were launched ahead (pre_sd, pre_key)
+    SegDesc pre_sd;
+    size_t pre_key[4];                // piece, offset, length, last_of_file of that segment
     double cand_bound;                // host-side bound on entries in the candidate buffer
     uint32_t n_table_host;
     unsigned long long tau_host;
@@ -311,6 +319,16 @@ extern "C" int ac_create(int device, ac_ctx **out) {
     CK(cudaMalloc(&c->d_jd, sizeof(JobDev)));
     CK(cudaHostAlloc(&c->h_jd, sizeof(JobDev), cudaHostAllocDefault));
     CK(cudaEventCreate(&c->ev_job0)); CK(cudaEventCreate(&c->ev_job1));
+    {
+        int lo = 0, hi = 0;   // the short parser kernels go in front of the hash kernel's remaining CTAs
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&c->s_aux, cudaStreamNonBlocking, hi));
+        CK(cudaEventCreateWithFlags(&c->ev_emit, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_pre, cudaEventDisableTiming));
+        // opt-in (AC_LOOKAHEAD=1): 4.44 -> 4.35 ms per C2 isolate in six of seven runs, 4.96 ms in one
+        const char *la = getenv("AC_LOOKAHEAD");
+        c->lookahead = la && atoi(la) != 0;
+    }
     { std::lock_guard<std::mutex> lk(g_ctx_mu); g_live_ctx.insert(c); }
     *out = c;
     return AC_OK;
@@ -332,7 +350,8 @@ extern "C" void ac_destroy(ac_ctx *c) {
     for (auto ev : c->ev_pool) cudaEventDestroy(ev);
     for (int i = 0; i < 3; i++) for (auto &p : c->prof[i]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     cudaEventDestroy(c->ev_job0); cudaEventDestroy(c->ev_job1);
-    cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_own);
+    cudaEventDestroy(c->ev_emit); cudaEventDestroy(c->ev_pre);
+    cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_own); cudaStreamDestroy(c->s_aux);
     delete c;
 }
 
@@ -340,6 +359,7 @@ extern "C" int ac_sync(ac_ctx *c) {
     if (!c) return fail(AC_E_PARAM, "ac_sync: ctx is NULL");
     CK(cudaSetDevice(c->dev));
     CK(cudaStreamSynchronize(c->s_copy));
+    CK(cudaStreamSynchronize(c->s_aux));
     CK(cudaStreamSynchronize(c->s_comp));
     return AC_OK;
 }
@@ -442,7 +462,7 @@ extern "C" int ac_sketch_begin(ac_ctx *c, int k, int sketch_size, uint32_t seed,
     j->use64 = k > 16 ? 1 : 0; j->seed = seed;
     j->cur_file = -1; j->file_open = false; j->cur_fmt = -1; j->tail_len = 0;
     j->pass_started = false; j->tau0 = 0; j->safe = false; j->table = false; j->passes = 0;
-    j->proc_piece = 0; j->proc_off = 0; j->pending = 0; j->first_of_stream = true;
+    j->proc_piece = 0; j->proc_off = 0; j->pending = 0; j->first_of_stream = true; j->pre_valid = false;
     j->cand_bound = 0; j->n_table_host = 0; j->tau_host = 0; j->bytes_done = 0; j->next_mark = 0; j->ended_local = false; j->table_pending = false;
     for (auto &s : c->slabs) s.used = 0;
     c->cur_slab = 0;
@@ -455,6 +475,7 @@ static void job_free(ac_job *j) {
     if (!j) return;
     ac_ctx *c = j->ctx;
     cudaStreamSynchronize(c->s_copy);
+    cudaStreamSynchronize(c->s_aux);   // a look-ahead launch of an aborted job may still be running
     cudaStreamSynchronize(c->s_comp);
     for (auto &p : j->pieces) if (p.ready) c->ev_pool.push_back(p.ready);
     if (c->active == j) c->active = nullptr;
@@ -523,26 +544,18 @@ static int start_pass(ac_job *j, unsigned long long tau0, bool safe) {
         c->ct.bshift = std::max(0, key_bits_for(tau0) - CT_BUCKET_BITS);
     }
     j->pass_started = true; j->tau0 = tau0; j->safe = safe; j->passes++;
-    j->proc_piece = 0; j->proc_off = 0; j->first_of_stream = true;
+    j->proc_piece = 0; j->proc_off = 0; j->first_of_stream = true; j->pre_valid = false;
+    CK(cudaEventRecord(c->ev_emit, c->s_comp));   // look-ahead launches of this pass start after its set-up
     j->cand_bound = 0; j->n_table_host = 0; j->tau_host = tau0; j->bytes_done = 0; j->next_mark = c->seg_bytes;
     return AC_OK;
 }
 
-// run K1 + K2 over bytes [off, off+len) of piece pi (len <= SEG_BYTES)
-static int run_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_of_file) {
+// descriptor of the segment [off, off+len) of piece pi, the next one of the pass (draws its epoch tag)
+static int build_segdesc(ac_job *j, size_t pi, size_t off, size_t len, bool last_of_file, SegDesc *out) {
     ac_ctx *c = j->ctx;
     const Piece &p = j->pieces[pi];
-    LaunchCtx lc{c->s_comp, &c->launches};
     const bool append_nl = last_of_file && p.append_nl;
     const size_t seg_len = len + (append_nl ? 1 : 0);
-    // candidate-buffer headroom: consolidate first when this segment could overflow it
-    const double frac = j->safe ? 1.0 : std::min(1.0, ((double)j->tau_host + 1.0) / ((double)space_max(j) + 1.0) * 2.0 + 1e-3);
-    const double seg_bound = j->safe ? (double)seg_len : (double)seg_len * frac + 65536.0;
-    if (!j->table && j->cand_bound > 0 && j->cand_bound + seg_bound + j->n_table_host > (double)c->sb.cap) {
-        int rc = consolidate(j);
-        if (rc) return rc;
-    }
-    if (p.ready) CK(cudaStreamWaitEvent(c->s_comp, p.ready, 0));
     SegDesc sd;
     const uintptr_t addr = (uintptr_t)(p.ptr + off);
     sd.base = (const uint8_t *)(addr & ~(uintptr_t)15);
@@ -561,11 +574,67 @@ static int run_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_o
     sd.epoch = c->seg_epoch;
     sd.ticket_base = j->ticket_base;
     if (sd.n_tiles > c->max_tiles) return fail(AC_E_INTERNAL, "segment of %zu bytes exceeds the tile arrays", seg_len);
+    *out = sd;
+    return AC_OK;
+}
+
+// FASTQ look-ahead: the segment that run_segment will be called with next is already known (its bytes are there), so
+// its k1q_count + k1q_scan go to s_aux now, beside the hash kernel of the segment just launched.  They read the text,
+// the parser state left by the previous k1q_scan and the tail of the stream k1q_emit just wrote, and they write the
+// tile arrays, the other parser-state slot and the carry at the head of the other Z buffer -- all free once the
+// previous k1q_emit is done (ev_emit); the hash kernel touches none of them.  Not in profile mode (the per-kernel
+// times of ac_last_times want one stream).
+static int prelaunch_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_of_file) {
+    ac_ctx *c = j->ctx;
+    const Piece &p = j->pieces[pi];
+    if (!c->lookahead || c->profile || p.fmt != FMT_FASTQ || j->pre_valid) return AC_OK;
+    SegDesc sd;
+    int rc = build_segdesc(j, pi, off, len, last_of_file, &sd);
+    if (rc) return rc;
+    CK(cudaStreamWaitEvent(c->s_aux, c->ev_emit, 0));
+    if (p.ready) CK(cudaStreamWaitEvent(c->s_aux, p.ready, 0));
+    LaunchCtx lc{c->s_aux, &c->launches};
+    launch_parse_segment(lc, sd, c->d_st1, c->d_st2, c->d_tcnt, c->tile_cap, c->d_jd, c->d_Z[(sd.serial + 1u) & 1u],
+                         c->d_Z[sd.serial & 1u], PARSE_PRE);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev_pre, c->s_aux));
+    j->pre_sd = sd; j->pre_valid = true;
+    j->pre_key[0] = pi; j->pre_key[1] = off; j->pre_key[2] = len; j->pre_key[3] = last_of_file ? 1 : 0;
+    return AC_OK;
+}
+
+// run K1 + K2 over bytes [off, off+len) of piece pi (len <= SEG_BYTES)
+static int run_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_of_file) {
+    ac_ctx *c = j->ctx;
+    const Piece &p = j->pieces[pi];
+    LaunchCtx lc{c->s_comp, &c->launches};
+    const bool append_nl = last_of_file && p.append_nl;
+    const size_t seg_len = len + (append_nl ? 1 : 0);
+    // candidate-buffer headroom: consolidate first when this segment could overflow it
+    const double frac = j->safe ? 1.0 : std::min(1.0, ((double)j->tau_host + 1.0) / ((double)space_max(j) + 1.0) * 2.0 + 1e-3);
+    const double seg_bound = j->safe ? (double)seg_len : (double)seg_len * frac + 65536.0;
+    if (!j->table && j->cand_bound > 0 && j->cand_bound + seg_bound + j->n_table_host > (double)c->sb.cap) {
+        int rc = consolidate(j);
+        if (rc) return rc;
+    }
+    SegDesc sd;
+    int part = PARSE_ALL;
+    if (j->pre_valid) {   // count + scan are in flight on s_aux
+        if (j->pre_key[0] != pi || j->pre_key[1] != off || j->pre_key[2] != len || j->pre_key[3] != (last_of_file ? 1u : 0u))
+            return fail(AC_E_INTERNAL, "look-ahead launched another segment than the one that follows");
+        sd = j->pre_sd; j->pre_valid = false; part = PARSE_POST;
+        CK(cudaStreamWaitEvent(c->s_comp, c->ev_pre, 0));
+    } else {
+        if (p.ready) CK(cudaStreamWaitEvent(c->s_comp, p.ready, 0));
+        int rc = build_segdesc(j, pi, off, len, last_of_file, &sd);
+        if (rc) return rc;
+    }
     uint8_t *Z = c->d_Z[sd.serial & 1u];
     {
         ProfScope ps(c, 0);
-        launch_parse_segment(lc, sd, c->d_st1, c->d_st2, c->d_tcnt, c->tile_cap, c->d_jd, c->d_Z[(sd.serial + 1u) & 1u], Z);
+        launch_parse_segment(lc, sd, c->d_st1, c->d_st2, c->d_tcnt, c->tile_cap, c->d_jd, c->d_Z[(sd.serial + 1u) & 1u], Z, part);
     }
+    if (c->lookahead && sd.fmt == FMT_FASTQ) CK(cudaEventRecord(c->ev_emit, c->s_comp));
     {
         ProfScope ps(c, 1);
         CountTable off;
@@ -600,20 +669,35 @@ static int run_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_o
     return AC_OK;
 }
 
-// process fed bytes; `all` = flush everything (job end), else only full segments once enough has
-// been fed, keeping HOLD_BACK bytes of a still-open file (EOF may trim trailing blank lines)
+// Is there a segment to process now?  `all` = flush everything (job end), else only full segments once enough has
+// been fed, keeping HOLD_BACK bytes of a still-open file (EOF may trim trailing blank lines).
+static bool segment_available(const ac_job *j, bool all, size_t *usable_out, bool *open_out) {
+    if (j->proc_piece >= j->pieces.size()) return false;
+    const Piece &p = j->pieces[j->proc_piece];
+    const bool is_last_piece = j->proc_piece + 1 == j->pieces.size();
+    const bool open = is_last_piece && !p.last_of_file;
+    const size_t avail = p.len - j->proc_off;
+    const size_t usable = open ? (avail > HOLD_BACK ? avail - HOLD_BACK : 0) : avail;
+    if (open && usable == 0) return false;
+    if (!all) {
+        if (j->pending < j->ctx->stream_seg_bytes + HOLD_BACK) return false;
+        if (open && usable < j->ctx->stream_seg_bytes) return false;
+    }
+    *usable_out = usable; *open_out = open;
+    return true;
+}
+// its extent (the pass must have started: the segment size depends on the pass kind)
+static void segment_extent(const ac_job *j, size_t usable, size_t *len, bool *seg_last) {
+    const Piece &p = j->pieces[j->proc_piece];
+    *len = std::min(usable, j->safe ? std::min(SEG_SAFE_BYTES, j->ctx->seg_bytes) : j->ctx->seg_bytes);
+    *seg_last = p.last_of_file && (j->proc_off + *len == p.len);
+}
+
+// process fed bytes, segment by segment
 static int pump(ac_job *j, bool all) {
-    while (j->proc_piece < j->pieces.size()) {
-        const Piece &p = j->pieces[j->proc_piece];
-        const bool is_last_piece = j->proc_piece + 1 == j->pieces.size();
-        const bool open = is_last_piece && !p.last_of_file;
-        const size_t avail = p.len - j->proc_off;
-        const size_t usable = open ? (avail > HOLD_BACK ? avail - HOLD_BACK : 0) : avail;
-        if (open && usable == 0) break;
-        if (!all) {
-            if (j->pending < j->ctx->stream_seg_bytes + HOLD_BACK) break;
-            if (open && usable < j->ctx->stream_seg_bytes) break;
-        }
+    size_t usable;
+    bool open;
+    while (segment_available(j, all, &usable, &open)) {
         if (!j->pass_started) {
             // the size fed so far decides the speculative threshold: big inputs start at 1/32 of
             // the hash space (64 expected candidates per 2,048-window sub-tile of K2, half its staging slots),
@@ -624,13 +708,25 @@ static int pump(ac_job *j, bool all) {
             int rc = start_pass(j, big ? (space_max(j) >> 5) : space_max(j), !big);
             if (rc) return rc;
         }
-        const size_t len = std::min(usable, j->safe ? std::min(SEG_SAFE_BYTES, j->ctx->seg_bytes) : j->ctx->seg_bytes);
-        const bool seg_last = p.last_of_file && (j->proc_off + len == p.len);
+        size_t len;
+        bool seg_last;
+        segment_extent(j, usable, &len, &seg_last);
+        const size_t piece_len = j->pieces[j->proc_piece].len;
         int rc = run_segment(j, j->proc_piece, j->proc_off, len, seg_last);
         if (rc) return rc;
         j->pending -= std::min(j->pending, len);
         j->proc_off += len;
-        if (j->proc_off == p.len && !open) { j->proc_piece++; j->proc_off = 0; }
+        if (j->proc_off == piece_len && !open) { j->proc_piece++; j->proc_off = 0; }
+        // the segment the next turn of this loop will take, if any: start its count + scan beside the hash kernel
+        size_t usable2;
+        bool open2;
+        if (segment_available(j, all, &usable2, &open2)) {
+            size_t len2;
+            bool last2;
+            segment_extent(j, usable2, &len2, &last2);
+            rc = prelaunch_segment(j, j->proc_piece, j->proc_off, len2, last2);
+            if (rc) return rc;
+        }
     }
     return AC_OK;
 }

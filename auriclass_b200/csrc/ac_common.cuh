@@ -115,8 +115,12 @@ struct LaunchCtx {
 };
 
 // kernels' host-side launchers (defined in the .cu files)
+// part: PARSE_ALL, or the two halves of a FASTQ segment -- PARSE_PRE = k1q_count + k1q_scan (they only need the text,
+// the previous segment's parser state and its emitted stream: ac_api.cu runs them on a second stream beside the
+// previous segment's hash kernel), PARSE_POST = k1q_emit.  FASTA (one kernel) belongs to PARSE_POST.
+enum { PARSE_ALL = 0, PARSE_PRE = 1, PARSE_POST = 2 };
 void launch_parse_segment(const LaunchCtx &lc, const SegDesc &sd, unsigned long long *st1, unsigned long long *st2,
-                          uint32_t *tile_arr, size_t tile_cap, JobDev *jd, const uint8_t *Zprev, uint8_t *Z);
+                          uint32_t *tile_arr, size_t tile_cap, JobDev *jd, const uint8_t *Zprev, uint8_t *Z, int part);
 // words of the FASTQ per-tile arrays for segments of up to max_tiles tiles; *tile_cap = padded entries per array
 size_t parse_tile_array_words(size_t max_tiles, size_t *tile_cap);
 // ps_slot: ParseState slot holding this segment's n_zbuf (= (serial + 1) & 1)

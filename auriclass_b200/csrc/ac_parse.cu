@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_fasta(SegDesc sd, JobDev *__res
 }  // namespace
 
 void launch_parse_segment(const LaunchCtx &lc, const SegDesc &sd, unsigned long long *st1, unsigned long long *st2,
-                          uint32_t *tile_arr, size_t tile_cap, JobDev *jd, const uint8_t *Zprev, uint8_t *Z) {
+                          uint32_t *tile_arr, size_t tile_cap, JobDev *jd, const uint8_t *Zprev, uint8_t *Z, int part) {
     // sd.n_tiles >= 1 (an empty segment still threads the parser state through its single tile)
     if (sd.fmt == FMT_FASTQ) {
         TileArrays ta;
@@ -604,11 +604,16 @@ void launch_parse_segment(const LaunchCtx &lc, const SegDesc &sd, unsigned long 
         for (int q = 0; q < 4; q++) ta.c[q] = tile_arr + (size_t)(q + 1) * tile_cap;
         ta.flag = tile_arr + 5 * tile_cap;
         ta.nlmask = reinterpret_cast<uint2 *>(tile_arr + 5 * tile_cap + 4);   // (8-byte aligned: cap is a multiple of 8192)
-        k1q_count<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, ta);
-        k1q_scan<<<1, SCAN_T, 0, lc.stream>>>(sd, ta, jd, Zprev, Z);
-        k1q_emit<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, ta, jd, Z);
-        *lc.launches += 3;
-    } else {
+        if (part != PARSE_POST) {
+            k1q_count<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, ta);
+            k1q_scan<<<1, SCAN_T, 0, lc.stream>>>(sd, ta, jd, Zprev, Z);
+            *lc.launches += 2;
+        }
+        if (part != PARSE_PRE) {
+            k1q_emit<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, ta, jd, Z);
+            ++*lc.launches;
+        }
+    } else if (part != PARSE_PRE) {
         k1_fasta<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, jd, st1, st2, Zprev, Z);
         ++*lc.launches;
     }

@@ -718,3 +718,40 @@ def test_flat_loop_redo_list_overflow(engine, k):
     sk = engine.sketch_bytes([buf], k=k, s=1000, m=2, chunk=3 << 20)
     assert_same_sketch(sk, ref)
     assert sk.info["passes"] == 1
+
+
+def test_fastq_lookahead_on_a_second_stream(reads):
+    """AC_LOOKAHEAD=1: k1q_count + k1q_scan of segment i+1 run on a second stream beside the hash kernel of segment i.
+    Many small segments (AC_SEG_MB=1), device-resident and host-fed, two files merged, a pass that is repeated after
+    a failed speculation, and the tau = max path: every sketch must equal the oracle's."""
+    import os
+    import torch
+    from auriclass_b200.mash_gpu import MashGPU, StreamStats
+    os.environ["AC_SEG_MB"] = "1"
+    os.environ["AC_LOOKAHEAD"] = "1"
+    try:
+        eng = MashGPU(0)
+    finally:
+        del os.environ["AC_SEG_MB"]
+        del os.environ["AC_LOOKAHEAD"]
+    try:
+        contigs = synth.genome(seed=17, scale=0.01)
+        fq = synth.fastq_reads(contigs, 120_000, seed=18).tobytes()   # ~38 MB, 38 segments
+        ref = oracle.sketch_parallel([fq], 27, 2000, 3)
+        t = torch.frombuffer(bytearray(fq), dtype=torch.uint8).cuda()
+        for _ in range(2):   # device-resident feed: every segment but the first is launched ahead
+            job = eng._begin(27, 2000, 42, 3, AC_MODE_READS)
+            _lib.check(eng.lib.ac_sketch_feed_device(job, t.data_ptr(), t.numel(), 0, 1))
+            assert_same_sketch(eng._end(job, "dev", 27, 2000, StreamStats()), ref)
+        assert_same_sketch(eng.sketch_bytes([fq], k=27, s=2000, m=3, chunk=3 << 20), ref)       # host-fed in 3 MB chunks
+        half = fq.rfind(b"\n@SYN", 0, len(fq) // 2) + 1
+        two = [fq[:half], fq[half:]]                                                           # two files, one sketch
+        assert_same_sketch(eng.sketch_bytes(two, k=27, s=2000, m=3, chunk=5 << 20), oracle.sketch_parallel(two, 27, 2000, 3))
+        # too few qualified hashes below 1/32 of the space: the pass is repeated with tau = max (look-ahead restarts)
+        low = synth.fastq_reads(contigs, 30_000, seed=19).tobytes()
+        sk = eng.sketch_bytes([low], k=27, s=50000, m=3, chunk=2 << 20)
+        assert_same_sketch(sk, oracle.sketch_parallel([low], 27, 50000, 3))
+        sk = eng.sketch_bytes(reads, k=27, s=50000, m=3)                                        # 5.2 MB, tau = max
+        assert_same_sketch(sk, oracle.sketch(reads, 27, 50000, 3))
+    finally:
+        eng.close()
