@@ -755,3 +755,35 @@ def test_fastq_lookahead_on_a_second_stream(reads):
         assert_same_sketch(sk, oracle.sketch(reads, 27, 50000, 3))
     finally:
         eng.close()
+
+
+def test_fastq_long_reads_spanning_tiles_and_subtiles(engine):
+    """Long-read FASTQ: sequence and quality lines of 3 kb .. 120 kb run across many 8 KiB parser tiles and
+    2,048-window hash sub-tiles (a header may sit anywhere inside a tile, a whole tile may be one line class).
+    Small input (tau = max, branchy loop) and a 12 MB one (count table, flat loop), both against the oracle."""
+    rng = np.random.default_rng(21)
+    g = _rand_seq(rng, 300_000)
+
+    def long_reads(n, lo, hi, n_rate=0.001):
+        out = []
+        for i in range(n):
+            L = int(rng.integers(lo, hi))
+            st = int(rng.integers(0, len(g) - L + 1))
+            seq = bytearray(g[st:st + L])
+            for p in rng.integers(0, L, int(L * n_rate)):
+                seq[int(p)] = ord("N")
+            q = bytes(rng.integers(33, 74, L, dtype=np.uint8))
+            q = (b"@" if i % 2 else b"+") + q[1:]
+            out.append(b"@lr%d runid=x\n" % i + bytes(seq) + b"\n+\n" + q + b"\n")
+        return b"".join(out)
+
+    small = long_reads(12, 3_000, 120_000)
+    assert len(small) < (4 << 20)
+    sk = engine.sketch_bytes([small], k=27, s=1000, m=1, chunk=100_003)
+    assert_same_sketch(sk, oracle.sketch([small], 27, 1000, 1))
+    big = long_reads(110, 3_000, 120_000)
+    assert len(big) > (8 << 20)
+    for k, m in ((27, 2), (16, 1)):
+        sk = engine.sketch_bytes([big], k=k, s=1000, m=m, chunk=3 << 20)
+        assert_same_sketch(sk, oracle.sketch_parallel([big], k, 1000, m))
+        assert sk.info["passes"] == 1
