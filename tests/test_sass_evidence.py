@@ -1,0 +1,80 @@
+"""Build-time evidence for the design claims of DESIGN.md section 5, read from the compiled objects (no GPU needed):
+K2 stages its sub-tile with a TMA bulk copy, its flat hot loop is still ONE basic block (a compiler or source change
+that re-introduces a branch per window would show here long before it shows in a bench), and nothing spills."""
+import re
+import shutil
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+OBJ = ROOT / "auriclass_b200" / "csrc" / "ac_hash.o"
+LOG = ROOT / "auriclass_b200" / "csrc" / "ac_hash.ptxas.log"
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="CUDA toolkit not on PATH")
+
+
+@pytest.fixture(scope="module")
+def k2_sass():
+    if not OBJ.exists():
+        import __graft_entry__ as g
+        g.build()
+    out = subprocess.run(["cuobjdump", "-sass", str(OBJ)], capture_output=True, text=True, check=True).stdout
+    funcs, name = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            funcs[name] = []
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(.*?);", line)
+        if m and name:
+            funcs[name].append(m.group(1).strip())
+    return funcs
+
+
+def _kernel(funcs, k, flat):
+    hits = [v for n, v in funcs.items() if f"k2_hashILi{k}ELb{1 if flat else 0}E" in n]
+    assert len(hits) == 1, f"k2_hash<{k}, {flat}> not found in ac_hash.o"
+    return hits[0]
+
+
+def _longest_straight_block(ins):
+    best = cur = 0
+    for t in ins:
+        if re.search(r"\b(BRA|CALL|BSSY|BSYNC|EXIT|RET|WARPSYNC)\b", t):
+            best, cur = max(best, cur), 0
+        else:
+            cur += 1
+    return max(best, cur)
+
+
+@pytest.mark.parametrize("k", [16, 21, 27, 32])
+def test_k2_uses_tma_and_flat_loop_is_one_block(k2_sass, k):
+    flat, branchy = _kernel(k2_sass, k, True), _kernel(k2_sass, k, False)
+    for ins in (flat, branchy):
+        assert any("UBLKCP" in t for t in ins), "no TMA bulk copy (UBLKCP)"
+        assert any("SYNCS" in t for t in ins), "no mbarrier"
+    # 8 windows x (14 IMAD.WIDE + ...) in one block; the branchy loop has a branch and a call per window
+    n_flat, n_branchy = _longest_straight_block(flat), _longest_straight_block(branchy)
+    assert n_flat >= 600, n_flat
+    assert n_branchy < n_flat // 3, (n_branchy, n_flat)
+    wide = sum(1 for t in flat if re.match(r"(@!?U?P\d\s+)?IMAD\.WIDE", t))
+    assert wide >= 8 * (14 if k > 16 else 10), wide   # the 64-bit multiplies of the 8 unrolled windows
+
+
+def test_k2_does_not_spill_at_the_production_k():
+    if not LOG.exists():
+        pytest.skip("no ptxas log (library built elsewhere)")
+    txt = LOG.read_text()
+    blocks = re.split(r"ptxas info\s+: Compiling entry function ", txt)
+    seen = 0
+    for b in blocks:
+        if re.match(r"'\S*k2_hashILi27ELb[01]E", b):
+            seen += 1
+            m = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", b)
+            assert m and m.group(2) == "0" and m.group(3) == "0", b[:300]
+            regs = int(re.search(r"Used (\d+) registers", b).group(1))
+            assert regs <= 64, regs   # 8 CTAs of 128 threads per SM
+    assert seen == 2
