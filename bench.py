@@ -463,6 +463,7 @@ def main() -> None:
                 "parallelism": "1 GPU" if world == 1 else f"read-block sharded over {world} GPUs, hash-range all-to-all + all-gather (NCCL)",
                 "n_kmers_per_gpu": int(n_kmers), "n_candidates_per_gpu": int(n_cand), "sketch_hashes": int(n_hashes),
                 "passes": int(passes),
+                "lookahead": os.environ.get("AC_LOOKAHEAD", "0") not in ("", "0"),   # k1q_count/scan of segment i+1 beside K2 of segment i
             },
             "e2e": {"value": world * bases_per_rank / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s",
                     "ms_per_step": e2e_ms, "wall_s_per_isolate": e2e_ms * 1e-3,
