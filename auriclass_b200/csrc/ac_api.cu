@@ -325,7 +325,7 @@ extern "C" int ac_create(int device, ac_ctx **out) {
         CK(cudaStreamCreateWithPriority(&c->s_aux, cudaStreamNonBlocking, hi));
         CK(cudaEventCreateWithFlags(&c->ev_emit, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_pre, cudaEventDisableTiming));
-        // opt-in (AC_LOOKAHEAD=1): 4.44 -> 4.35 ms per C2 isolate in six of seven runs, 4.96 ms in one
+        // opt-in (AC_LOOKAHEAD=1): 4.44 -> 4.35 ms per C2 isolate in seven of eight runs, 4.96 ms in one
         const char *la = getenv("AC_LOOKAHEAD");
         c->lookahead = la && atoi(la) != 0;
     }
