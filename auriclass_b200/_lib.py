@@ -76,6 +76,8 @@ SIGNATURES = {
     "ac_dist_batch": (C.c_int, [_vp, _vp, C.POINTER(_vp), C.c_int, _vp, _vp, _vp, _vp]),
     "ac_dist_pairs": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "ac_launch_count": (C.c_uint64, [_vp]),
+    "ac_timer_start": (C.c_int, [_vp]),
+    "ac_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "ac_set_profile": (C.c_int, [_vp, C.c_int]),
     "ac_last_job_times": (C.c_int, [_vp, C.POINTER(C.c_float * 4)]),
     "ac_int_peak": (C.c_int, [_vp, _dp]),

@@ -104,6 +104,7 @@ struct ac_ctx {
     std::vector<SketchBuf> sk_pool;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[3];
     cudaEvent_t ev_job0, ev_job1;
+    cudaEvent_t ev_t0, ev_t1;  // ac_timer_start / ac_timer_stop
     // FASTQ look-ahead: k1q_count + k1q_scan of the next segment run on s_aux beside the hash kernel of this one
     cudaStream_t s_aux;
     cudaEvent_t ev_emit;       // on s_comp: the last k1q_emit (or the start of the pass) is done -> the tile arrays are free
@@ -275,6 +276,8 @@ static int alloc_select(ac_ctx *c, size_t sk_cap) {
 
 extern "C" void ac_sketch_abort(ac_job *j);
 
+static int create_impl(ac_ctx *c, int device);
+
 extern "C" int ac_create(int device, ac_ctx **out) {
     if (!out) return fail(AC_E_PARAM, "ac_create: out is NULL");
     *out = nullptr;
@@ -283,7 +286,23 @@ extern "C" int ac_create(int device, ac_ctx **out) {
     if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(AC_E_CUDA, "no CUDA device visible: libauriclass_cuda.so has no CPU path"); }
     if (device < 0 || device >= n) return fail(AC_E_PARAM, "device %d out of range (0..%d)", device, n - 1);
     CK(cudaSetDevice(device));
-    ac_ctx *c = new ac_ctx();
+    ac_ctx *c = new ac_ctx();   // value-initialised: every handle starts out null, so a partial context can be destroyed
+    c->dev = device;
+    const int rc = create_impl(c, device);
+    if (rc) {   // streams, events and buffers made so far go the way of a finished context (g_err keeps the cause)
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));
+        ac_destroy(c);
+        cudaGetLastError();
+        memcpy(g_err, keep, sizeof(keep));
+        return rc;
+    }
+    { std::lock_guard<std::mutex> lk(g_ctx_mu); g_live_ctx.insert(c); }
+    *out = c;
+    return AC_OK;
+}
+
+static int create_impl(ac_ctx *c, int device) {
     c->dev = device; c->launches = 0; c->profile = false; c->sb_ok = false; c->active = nullptr;
     c->cur_slab = 0; c->sk_cap = 0;
     memset(c->last_ms, 0, sizeof(c->last_ms));
@@ -319,6 +338,7 @@ extern "C" int ac_create(int device, ac_ctx **out) {
     CK(cudaMalloc(&c->d_jd, sizeof(JobDev)));
     CK(cudaHostAlloc(&c->h_jd, sizeof(JobDev), cudaHostAllocDefault));
     CK(cudaEventCreate(&c->ev_job0)); CK(cudaEventCreate(&c->ev_job1));
+    CK(cudaEventCreate(&c->ev_t0)); CK(cudaEventCreate(&c->ev_t1));
     {
         int lo = 0, hi = 0;   // the short parser kernels go in front of the hash kernel's remaining CTAs
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -329,8 +349,6 @@ extern "C" int ac_create(int device, ac_ctx **out) {
         const char *la = getenv("AC_LOOKAHEAD");
         c->lookahead = la && atoi(la) != 0;
     }
-    { std::lock_guard<std::mutex> lk(g_ctx_mu); g_live_ctx.insert(c); }
-    *out = c;
     return AC_OK;
 }
 
@@ -349,9 +367,9 @@ extern "C" void ac_destroy(ac_ctx *c) {
     cudaFreeHost(c->h_dist); cudaFreeHost(c->h_p); cudaFreeHost(c->h_common); cudaFreeHost(c->h_denom); cudaFreeHost(c->h_qmeta);
     for (auto ev : c->ev_pool) cudaEventDestroy(ev);
     for (int i = 0; i < 3; i++) for (auto &p : c->prof[i]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-    cudaEventDestroy(c->ev_job0); cudaEventDestroy(c->ev_job1);
-    cudaEventDestroy(c->ev_emit); cudaEventDestroy(c->ev_pre);
-    cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_own); cudaStreamDestroy(c->s_aux);
+    for (cudaEvent_t ev : {c->ev_job0, c->ev_job1, c->ev_emit, c->ev_pre, c->ev_t0, c->ev_t1}) if (ev) cudaEventDestroy(ev);
+    for (cudaStream_t st : {c->s_copy, c->s_own, c->s_aux}) if (st) cudaStreamDestroy(st);
+    cudaGetLastError();
     delete c;
 }
 
@@ -375,6 +393,23 @@ extern "C" int ac_set_stream(ac_ctx *c, void *stream, int injected) {
 }
 
 extern "C" uint64_t ac_launch_count(const ac_ctx *c) { return c ? c->launches : 0; }
+
+// CUDA-event stopwatch on the compute stream: brackets whatever the caller enqueues in between (a sketch job and the
+// dist call that follows it, collectives a caller put on an injected stream included)
+extern "C" int ac_timer_start(ac_ctx *c) {
+    if (!c) return fail(AC_E_PARAM, "ac_timer_start: ctx is NULL");
+    CK(cudaSetDevice(c->dev));
+    CK(cudaEventRecord(c->ev_t0, c->s_comp));
+    return AC_OK;
+}
+extern "C" int ac_timer_stop(ac_ctx *c, float *ms) {
+    if (!c || !ms) return fail(AC_E_PARAM, "ac_timer_stop: NULL argument");
+    CK(cudaSetDevice(c->dev));
+    CK(cudaEventRecord(c->ev_t1, c->s_comp));
+    CK(cudaEventSynchronize(c->ev_t1));
+    CK(cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
+    return AC_OK;
+}
 
 extern "C" int ac_set_profile(ac_ctx *c, int on) {
     if (!c) return fail(AC_E_PARAM, "ctx is NULL");
@@ -639,8 +674,9 @@ static int run_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_o
         ProfScope ps(c, 1);
         CountTable off;
         memset(&off, 0, sizeof(off));
-        launch_hash_segment(lc, j->k, Z, (uint32_t)(Z_CARRY + seg_len + 1), (int)((sd.serial + 1u) & 1u), c->d_jd, c->sb.keys_a,
-                            c->sb.cap, j->seed, j->use64, j->table ? c->ct : off);
+        if (!launch_hash_segment(lc, j->k, Z, (uint32_t)(Z_CARRY + seg_len + 1), (int)((sd.serial + 1u) & 1u), c->d_jd, c->sb.keys_a,
+                                 c->sb.cap, j->seed, j->use64, j->table ? c->ct : off))
+            return fail(AC_E_PARAM, "this build of libauriclass_cuda.so has no hash kernel for k = %d", j->k);
     }
     j->seg_serial++;
     if (sd.fmt == FMT_FASTA) j->ticket_base += sd.n_tiles;  // only k1_fasta draws tile tickets

@@ -125,7 +125,8 @@ void launch_parse_segment(const LaunchCtx &lc, const SegDesc &sd, unsigned long 
 size_t parse_tile_array_words(size_t max_tiles, size_t *tile_cap);
 // ps_slot: ParseState slot holding this segment's n_zbuf (= (serial + 1) & 1)
 // ct.mask != 0: candidates are inserted into the count table instead of being appended to cand
-void launch_hash_segment(const LaunchCtx &lc, int k, const uint8_t *Z, uint32_t max_zbuf, int ps_slot, JobDev *jd,
+// false: this build has no kernel for k (nothing launched)
+bool launch_hash_segment(const LaunchCtx &lc, int k, const uint8_t *Z, uint32_t max_zbuf, int ps_slot, JobDev *jd,
                          unsigned long long *cand, unsigned long long cand_cap, uint32_t seed, int use64,
                          const CountTable &ct);
 

@@ -392,11 +392,9 @@ void launch_dist(const LaunchCtx &lc, const unsigned long long *ref_hashes, cons
     size_t smem = ((max_q_n + D_SAMPLE - 1) / D_SAMPLE) * sizeof(u64);
     if (smem > (size_t)D_MAX_SAMPLES * sizeof(u64)) smem = (size_t)D_MAX_SAMPLES * sizeof(u64);
     if (smem < 64) smem = 64;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k5_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, D_MAX_SAMPLES * (int)sizeof(u64));
-        attr_set = true;
-    }
+    // beyond the 48 KB default the opt-in is needed -- per device (function attributes live in the context, not in the
+    // process), so it is set whenever such a launch is made; a failure surfaces as the launch error the caller checks
+    if (smem > 48u * 1024u) cudaFuncSetAttribute(k5_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, D_MAX_SAMPLES * (int)sizeof(u64));
     k5_dist<<<n_refs * n_q, D_THREADS, smem, lc.stream>>>(ref_hashes, ref_off, ref_len, n_refs, q_hashes, q_n, q_len, k,
                                                        sketch_size, d_dist, d_p, d_common, d_denom);
     ++*lc.launches;

@@ -401,7 +401,7 @@ void launch_k(const LaunchCtx &lc, const uint8_t *Z, uint32_t max_zbuf, int ps_s
 
 #define AC_K_CASE(KK) case KK: launch_k<KK>(lc, Z, max_zbuf, ps_slot, jd, cand, cand_cap, seed, ct); break;
 
-void launch_hash_segment(const LaunchCtx &lc, int k, const uint8_t *Z, uint32_t max_zbuf, int ps_slot, JobDev *jd,
+bool launch_hash_segment(const LaunchCtx &lc, int k, const uint8_t *Z, uint32_t max_zbuf, int ps_slot, JobDev *jd,
                          unsigned long long *cand, unsigned long long cand_cap, uint32_t seed, int use64,
                          const CountTable &ct) {
     (void)use64;  // the hash width follows k (CandSink<(K > 16)>)
@@ -414,8 +414,9 @@ void launch_hash_segment(const LaunchCtx &lc, int k, const uint8_t *Z, uint32_t 
         AC_K_CASE(17) AC_K_CASE(18) AC_K_CASE(19) AC_K_CASE(20) AC_K_CASE(21) AC_K_CASE(22) AC_K_CASE(23) AC_K_CASE(24)
         AC_K_CASE(25) AC_K_CASE(26) AC_K_CASE(27) AC_K_CASE(28) AC_K_CASE(29) AC_K_CASE(30) AC_K_CASE(31) AC_K_CASE(32)
 #endif
-        default: break;
+        default: return false;   // k outside the instantiated set (development builds with AC_ONLY_K27): nothing was launched
     }
+    return true;
 }
 
 }  // namespace ac

@@ -2,8 +2,8 @@
 //
 // Replaces Mash's Sketch.cpp addMinHashes()/getHash() (external binary called at
 // auriclass/classes.py:576-596 and :696-713; algorithm: SURVEY.md App. A.3).
-// Everything here is __host__ __device__ so tests/test_core_host.py can run the
-// very same arithmetic on the CPU (through csrc/hostcheck.cpp) against the oracle;
+// Everything here is __host__ __device__ so tests/test_host.py can run the
+// very same arithmetic on the CPU (through tests/hostcheck/hostcheck.cpp) against the oracle;
 // the product path only ever calls it from device code.
 //
 // Data model.  K1 hands K2 a *sanitised compacted base stream* Z: one byte per

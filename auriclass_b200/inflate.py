@@ -74,6 +74,62 @@ def _inflate_blocks(buf: bytes, blocks: List[Tuple[int, int, int]]) -> Tuple[byt
     return b"".join(parts), time.perf_counter() - t0
 
 
+BGZF_WINDOW = 16 << 20     # compressed bytes read per step of the BGZF path (memory stays flat: ~2 windows + look-ahead)
+
+
+def _iter_bgzf(f, head: bytes, threads: int, add):
+    """BGZF path: the file is read in windows, each window's complete blocks are inflated on the pool in file order.
+    Generator; its return value is None at a clean end of file, else the file offset where the block chain stopped
+    being well-formed BGZF (the caller continues from there with the sequential inflater: a BGZF file is a
+    multi-member gzip file, and so is whatever follows a block boundary)."""
+    pos = 0                   # file offset of buf[0]
+    buf = head
+    eof = False
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        window: "queue.Queue" = queue.Queue()
+
+        def drain(limit: int):
+            while window.qsize() > limit:
+                t0 = time.perf_counter()
+                data, dt = window.get().result()
+                add("inflate_wall_s", time.perf_counter() - t0)
+                add("inflate_s", dt)
+                if data:
+                    yield data
+
+        while True:
+            if not eof and len(buf) < BGZF_WINDOW:
+                t0 = time.perf_counter()
+                more = f.read(BGZF_WINDOW)
+                add("read_s", time.perf_counter() - t0)
+                eof = not more
+                buf += more
+            # complete blocks at the head of buf
+            table, off, n, bad = [], 0, len(buf), False
+            while off < n:
+                size = _bgzf_block_size(buf[off:off + 64])
+                if size is None or size < 26:
+                    bad = n - off >= 64 or eof          # a short tail of an unfinished read is not a verdict yet
+                    break
+                if off + size > n:
+                    bad = eof                             # truncated last block
+                    break
+                xlen = struct.unpack_from("<H", buf, off + 10)[0]
+                table.append((off, size, 12 + xlen))
+                off += size
+            for i in range(0, len(table), BGZF_BATCH):
+                window.put(pool.submit(_inflate_blocks, buf, table[i:i + BGZF_BATCH]))
+                yield from drain(2 * threads)             # bounded look-ahead
+            if bad:
+                yield from drain(0)
+                return pos + off
+            buf = buf[off:]
+            pos += off
+            if eof and not buf:
+                yield from drain(0)
+                return None
+
+
 def iter_inflated(path: PathLike, stats=None, threads: Optional[int] = None) -> Iterator[bytes]:
     """Inflated bytes of `path`, in order, as a sequence of chunks."""
     threads = threads or default_threads()
@@ -97,35 +153,14 @@ def iter_inflated(path: PathLike, stats=None, threads: Optional[int] = None) -> 
                     return
                 yield chunk
         if _bgzf_block_size(head) is not None:                # ---- BGZF: parallel block inflate
-            t0 = time.perf_counter()
-            buf = head + f.read()
-            add("read_s", time.perf_counter() - t0)
-            table = bgzf_block_table(buf)
-            if table is not None:
-                batches = [table[i:i + BGZF_BATCH] for i in range(0, len(table), BGZF_BATCH)]
-                with ThreadPoolExecutor(max_workers=threads) as pool:
-                    window: "queue.Queue" = queue.Queue()
-                    it = iter(batches)
-                    for _ in range(2 * threads):              # bounded look-ahead keeps memory flat
-                        b = next(it, None)
-                        if b is None:
-                            break
-                        window.put(pool.submit(_inflate_blocks, buf, b))
-                    while not window.empty():
-                        t0 = time.perf_counter()
-                        data, dt = window.get().result()
-                        add("inflate_wall_s", time.perf_counter() - t0)
-                        add("inflate_s", dt)
-                        b = next(it, None)
-                        if b is not None:
-                            window.put(pool.submit(_inflate_blocks, buf, b))
-                        if data:
-                            yield data
+            resume = yield from _iter_bgzf(f, head, threads, add)
+            if resume is None:
                 return
-            f.seek(0)                                         # malformed block chain: fall back to sequential inflate
-            head = b""
+            f.seek(resume)                                    # malformed block chain: sequential inflate from there
+            resumed = True
         else:
             f.seek(0)
+            resumed = False
 
         # ---- sequential gzip (single or multi member): one background thread, bounded queue
         q: "queue.Queue" = queue.Queue(maxsize=4)
@@ -133,21 +168,40 @@ def iter_inflated(path: PathLike, stats=None, threads: Optional[int] = None) -> 
 
         def producer() -> None:
             try:
-                dec = zlib.decompressobj(wbits=47)
+                dec = None
+                at_boundary = True     # between members: a gzip header must follow, anything else is trailing garbage
+                n_members = 0
+                src = b""
                 while not stop.is_set():
                     t0 = time.perf_counter()
-                    src = f.read(1 << 20)
+                    more = f.read(1 << 20)
                     add("read_s", time.perf_counter() - t0)
-                    if not src:
-                        if not dec.eof:
+                    src += more
+                    if not more:
+                        if not at_boundary or (src and src == b"\x1f\x8b"[:len(src)]):
                             raise zlib.error("gzip stream ends inside a member")
-                        break
+                        break                                  # (a lone trailing byte that is not a header start: garbage)
                     while src:
                         t0 = time.perf_counter()
-                        if dec.eof:                            # next member (concatenated members are legal)
+                        if at_boundary:
+                            # what follows a finished member: another member (concatenated members are legal) or
+                            # padding / garbage, which zlib's gzread -- what mash reads its inputs with -- ignores
+                            if len(src) < 2:
+                                break                          # decide once two bytes are there
+                            if src[:2] != b"\x1f\x8b":
+                                if n_members == 0 and not resumed:
+                                    raise zlib.error("not a gzip stream")
+                                src = b""
+                                stop.set()
+                                break
                             dec = zlib.decompressobj(wbits=47)
+                            at_boundary = False
+                            n_members += 1
                         out = dec.decompress(src, READ_BYTES)
-                        src = dec.unconsumed_tail if not dec.eof else dec.unused_data
+                        if dec.eof:
+                            src, at_boundary = dec.unused_data, True
+                        else:
+                            src = dec.unconsumed_tail
                         add("inflate_s", time.perf_counter() - t0)
                         if out:
                             q.put(out)

@@ -176,6 +176,13 @@ int ac_dist_pairs(ac_ctx *ctx, const ac_refs *a, int i0, int ni, const ac_refs *
 /* ---- instrumentation ------------------------------------------------- */
 /* Kernel launches issued by this context since creation (bench.py gpu_launches). */
 uint64_t ac_launch_count(const ac_ctx *ctx);
+/* CUDA-event stopwatch on the context's compute stream: ac_timer_start records an event, ac_timer_stop records a
+ * second one, waits for it and returns the device time between the two in milliseconds -- everything enqueued on the
+ * compute stream in between (a sketch job, the dist call after it; on an injected stream also the caller's
+ * collectives).  bench.py times a whole per-isolate step with it (the reference times the `mash` child processes,
+ * auriclass/classes.py:100-104, :592-596, from outside in the same way). */
+int ac_timer_start(ac_ctx *ctx);
+int ac_timer_stop(ac_ctx *ctx, float *ms);
 /* Record CUDA events around every kernel group of subsequent jobs (off by default). */
 int ac_set_profile(ac_ctx *ctx, int on);
 /* Device time (ms, CUDA events on the compute stream) the last finished job

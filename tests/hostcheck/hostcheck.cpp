@@ -1,4 +1,4 @@
-// hostcheck.cpp -- CPU harness around kmer_core.cuh for tests/test_core_host.py.
+// hostcheck.cpp -- CPU harness around kmer_core.cuh for tests/test_host.py (test infrastructure, not product).
 //
 // TEST INFRASTRUCTURE.  Runs the *same* __host__ __device__ arithmetic that kernel
 // K2 executes (slices of the sanitised base stream, canonical strand choice,
@@ -12,7 +12,7 @@
 #include <utility>
 #include <vector>
 
-#include "kmer_core.cuh"
+#include "../../auriclass_b200/csrc/kmer_core.cuh"
 
 namespace {
 struct Collect {

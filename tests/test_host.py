@@ -23,7 +23,7 @@ D = "tests/data/"
 # ----------------------------------------------------------------- kmer_core.cuh on the CPU
 @pytest.fixture(scope="module")
 def hostcheck():
-    so = ROOT / "auriclass_b200" / "csrc" / "libac_hostcheck.so"
+    so = ROOT / "tests" / "hostcheck" / "libac_hostcheck.so"
     if not so.exists():
         import __graft_entry__ as g
         g.build()

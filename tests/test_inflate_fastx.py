@@ -99,3 +99,56 @@ def test_pyfastx_stand_in_sniffs_like_the_reference_tests(tmp_path):
     mod = fastx.install_pyfastx_stub()
     import pyfastx
     assert pyfastx is mod or hasattr(pyfastx, "Fasta")
+
+
+@pytest.mark.parametrize("pad", [b"\0" * 512, b"\0", b"garbage after the last member\n" * 40])
+def test_bytes_after_the_last_gzip_member_are_ignored_like_gzread(tmp_path, pad):
+    """zlib's gzread (what mash reads its inputs with) and Python's gzip module both accept zero / tar padding after
+    the last member; so does the host streamer (single member, several members, BGZF)."""
+    data = _text(400_000, seed=5)
+    for name, blob in (("single", gzip.compress(data, 3)),
+                       ("multi", gzip.compress(data[:100_000], 1) + gzip.compress(data[100_000:], 1)),
+                       ("bgzf", inflate.bgzf_compress(data))):
+        p = tmp_path / name
+        p.write_bytes(blob + pad)
+        assert b"".join(inflate.iter_inflated(p, threads=2)) == data, name
+        if pad[:1] == b"\0":
+            assert gzip.decompress(blob + pad) == data       # the behaviour being matched
+
+
+def test_bgzf_is_read_in_windows_not_as_one_blob(tmp_path, monkeypatch):
+    """Memory stays flat: the BGZF path reads the file window by window (blocks straddle window boundaries), and a
+    chain that stops being BGZF half way (here: an ordinary gzip member appended) continues on the sequential path."""
+    data = _text(3_000_000, seed=6)
+    blob = inflate.bgzf_compress(data)
+    p = tmp_path / "w.gz"
+    p.write_bytes(blob)
+    monkeypatch.setattr(inflate, "BGZF_WINDOW", 100_003)
+    reads = []
+    real_open = open
+
+    class Spy:
+        def __init__(self, f):
+            self.f = f
+
+        def read(self, n=-1):
+            reads.append(n)
+            return self.f.read(n)
+
+        def __getattr__(self, a):
+            return getattr(self.f, a)
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return self.f.__exit__(*a)
+
+    monkeypatch.setattr("builtins.open", lambda *a, **k: Spy(real_open(*a, **k)))
+    st = StreamStats()
+    assert b"".join(inflate.iter_inflated(p, st, threads=3)) == data
+    assert max(reads) <= 100_003 and -1 not in reads and len(reads) > len(blob) // 100_003
+    assert st.inflate_s > 0
+    tail = _text(200_000, seed=7)
+    p.write_bytes(blob + gzip.compress(tail, 1))
+    assert b"".join(inflate.iter_inflated(p, threads=3)) == data + tail
