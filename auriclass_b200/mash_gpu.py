@@ -130,6 +130,49 @@ class DistRow:
         return f"{self.reference}\t{self.query}\t{fmt_g(self.distance)}\t{fmt_g(self.pvalue)}\t{self.common}/{self.denom}"
 
 
+class _PinnedFeeder:
+    """Copies host bytes of ONE file through the engine's two pinned staging buffers into ac_sketch_feed; the copy into
+    buffer B overlaps the H2D transfer of buffer A."""
+
+    def __init__(self, engine: "MashGPU", job: int, file_idx: int, st: StreamStats):
+        self.eng, self.job, self.file_idx, self.st = engine, job, file_idx, st
+        self.bufs = engine._staging()
+        self.which = 0
+        self.in_flight = 0
+        self.fill = 0
+
+    def _feed(self, n: int, eof: int) -> None:
+        t0 = time.perf_counter()
+        lib = self.eng.lib
+        check(lib.ac_sketch_feed(self.job, self.bufs[self.which][0], n, self.file_idx, eof))
+        self.st.bytes_in += n
+        self.which ^= 1
+        self.in_flight += 1
+        if self.in_flight >= 2 and not eof:
+            # both staging buffers are in flight: wait before overwriting the older one
+            check(lib.ac_sketch_feed_wait(self.job))
+            self.in_flight = 0
+        self.st.feed_s += time.perf_counter() - t0
+
+    def write(self, data) -> None:
+        mv = memoryview(data)
+        off = 0
+        while off < len(mv):
+            n = min(CHUNK_BYTES - self.fill, len(mv) - off)
+            self.bufs[self.which][1][self.fill:self.fill + n] = mv[off:off + n]
+            self.fill += n
+            off += n
+            if self.fill == CHUNK_BYTES:
+                self._feed(self.fill, 0)
+                self.fill = 0
+
+    def close(self) -> None:
+        """End of the file: the rest of the staging buffer goes out with the EOF mark."""
+        self._feed(self.fill, 1)
+        self.fill = 0
+        check(self.eng.lib.ac_sketch_feed_wait(self.job))
+
+
 class MashGPU:
     """One device context (ac_ctx).  Not thread safe; one per thread / rank."""
 
@@ -141,6 +184,7 @@ class MashGPU:
         self.device = device
         self._pinned: List[int] = []
         self._refs_cache = {}
+        self._sharders = {}
         self.inflate_threads: Optional[int] = None   # None: inflate.default_threads()
 
     # ---------------------------------------------------------------- plumbing
@@ -152,6 +196,9 @@ class MashGPU:
 
     def close(self) -> None:
         if self._ctx:
+            for sh in self._sharders.values():
+                sh.close()
+            self._sharders.clear()
             for r in self._refs_cache.values():
                 r.free()
             self._refs_cache.clear()
@@ -217,37 +264,10 @@ class MashGPU:
     def _stream_file(self, job: int, path: PathLike, file_idx: int, st: StreamStats) -> None:
         """Duty (2) of the host: file bytes -> (inflate, inflate.py) -> pinned buffer -> ac_sketch_feed."""
         from . import inflate
-        bufs = self._staging()
-        which = 0
-        in_flight = 0
-
-        def feed(n: int, eof: int) -> None:
-            nonlocal which, in_flight
-            t0 = time.perf_counter()
-            check(self.lib.ac_sketch_feed(job, bufs[which][0], n, file_idx, eof))
-            st.bytes_in += n
-            which ^= 1
-            in_flight += 1
-            if in_flight >= 2 and not eof:
-                # both staging buffers are in flight: wait before overwriting the older one
-                check(self.lib.ac_sketch_feed_wait(job))
-                in_flight = 0
-            st.feed_s += time.perf_counter() - t0
-
-        fill = 0
+        feeder = _PinnedFeeder(self, job, file_idx, st)
         for data in inflate.iter_inflated(path, st, self.inflate_threads):
-            mv = memoryview(data)
-            off = 0
-            while off < len(mv):
-                n = min(CHUNK_BYTES - fill, len(mv) - off)
-                bufs[which][1][fill:fill + n] = mv[off:off + n]
-                fill += n
-                off += n
-                if fill == CHUNK_BYTES:
-                    feed(fill, 0)
-                    fill = 0
-        feed(fill, 1)
-        check(self.lib.ac_sketch_feed_wait(job))
+            feeder.write(data)
+        feeder.close()
 
     def _end(self, job: int, name: str, k: int, s: int, st: StreamStats) -> GpuSketch:
         sk = C.c_void_p()
@@ -272,6 +292,53 @@ class MashGPU:
             self.lib.ac_sketch_abort(job)
             raise
         sk = self._end(job, str(paths[0]), k, s, st)
+        st.total_s = time.perf_counter() - t0
+        return sk
+
+    def sharder(self, group=None):
+        """The exchange protocol object of this engine for a torch.distributed process group (made once per group)."""
+        import torch.distributed as dist
+        from .sharded import ShardedSketcher
+        key = id(group)
+        sh = self._sharders.get(key)
+        if sh is None:
+            sh = ShardedSketcher(self, dist.get_rank(group), dist.get_world_size(group), group)
+            self._sharders[key] = sh
+        return sh
+
+    def sketch_reads_sharded(self, paths: Sequence[PathLike], k: int = 27, s: int = 50000, m: int = 3, seed: int = 42,
+                             group=None, block_bytes: Optional[int] = None) -> GpuSketch:
+        """`mash sketch -r -m m -k k -s s paths...` over the ranks of a torch.distributed process group (one rank per
+        GPU; BASELINE.json configs[2]).  COLLECTIVE: every rank calls it with the same arguments and gets the same
+        sketch.  The inflated streams are cut at record boundaries into read blocks (readblocks.py), block b goes to
+        rank b mod P; each rank parses and hashes its blocks, then the ranks make the counts exact by one hash-range
+        exchange (sharded.py).  k-mers never span records, so the result is the sketch of all the reads."""
+        import torch.distributed as dist
+        from . import inflate
+        from .readblocks import DEFAULT_BLOCK_BYTES, ReadBlockCutter
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        sh = self.sharder(group)
+        st = StreamStats()
+        t0 = time.perf_counter()
+        cutter = ReadBlockCutter(block_bytes or DEFAULT_BLOCK_BYTES)
+        job = self._begin(k, s, seed, m, AC_MODE_READS)
+        failure = None
+        try:
+            for i, p in enumerate(paths):
+                cutter.start_file()
+                feeder = _PinnedFeeder(self, job, i, st)
+                for data in inflate.iter_inflated(p, st, self.inflate_threads):
+                    for bi, piece in cutter.feed(data):
+                        if bi % world == rank:
+                            feeder.write(piece)
+                for bi, piece in cutter.end_file():
+                    if bi % world == rank:
+                        feeder.write(piece)
+                feeder.close()
+        except BaseException as e:    # the other ranks are on their way into the exchange: tell them there, then raise
+            failure = e
+        sk = sh.finish(job, k, s, m, name=str(paths[0]), failure=failure)
+        sk.stats = st
         st.total_s = time.perf_counter() - t0
         return sk
 

@@ -57,6 +57,14 @@ def range_bounds(tau_cut: int, n_ranges: int) -> List[int]:
     return [(span * r + n_ranges - 1) // n_ranges for r in range(n_ranges)]
 
 
+class PeerFailure(_lib.AcError):
+    """Another rank of the group failed before the exchange (bad input in its read blocks, CUDA error, ...): raised
+    on every rank at the first collective, so nobody is left waiting."""
+
+    def __init__(self, n_failed: int):
+        super().__init__(_lib.AC_E_STATE, f"sharded sketch aborted: {n_failed} rank(s) of the group failed before the exchange")
+
+
 @dataclass
 class LocalTable:
     """A rank's exact (hash, count) table of everything <= tau, ascending; bit patterns of u64 / u32
@@ -94,7 +102,14 @@ class CudaTableBackend:
         spec = C.c_int()
         info = SketchInfo()
         try:
-            check(self.lib.ac_sketch_end_local(job, C.byref(n), C.byref(tau), C.byref(spec), C.byref(info)))
+            try:
+                check(self.lib.ac_sketch_end_local(job, C.byref(n), C.byref(tau), C.byref(spec), C.byref(info)))
+            except BaseException:
+                try:
+                    tau_cut_fn((1 << 64) - 1, False)   # the others are waiting in the all-reduce: tell them
+                except PeerFailure:
+                    pass
+                raise
             tau_cut = tau_cut_fn(int(tau.value))
             begins = (C.c_uint64 * (n_ranges + 1))()
             check(self.lib.ac_job_table_ranges(job, tau_cut, n_ranges, begins))
@@ -143,16 +158,34 @@ class ShardedSketcher:
         self.last_exchange = {}
         self._mark = None   # optional callable(name): phase timing hook (tools/time_sharded.py)
 
-    # -- step 1
-    def _tau_cut(self, tau_local: int) -> int:
-        t = torch.tensor([u64_to_ordered_i64(tau_local)], dtype=torch.int64, device=self.device)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
-        return ordered_i64_to_u64(int(t.item()))
+    def close(self) -> None:
+        if hasattr(self.backend, "unshare_stream"):
+            self.backend.unshare_stream()
 
-    def finish(self, job, k: int, s: int, m: int, name: str = "reads"):
-        """Collective: every rank calls it with its own job; every rank returns the same sketch."""
+    # -- step 1 (also the point where the ranks agree that everybody got this far)
+    def _tau_cut(self, tau_local: int, ok: bool = True) -> int:
+        t = torch.tensor([u64_to_ordered_i64(tau_local), 0 if ok else -1], dtype=torch.int64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        tau_cut, worst = t.tolist()
+        if worst < 0:
+            f = torch.tensor([0 if ok else 1], dtype=torch.int64, device=self.device)
+            dist.all_reduce(f, op=dist.ReduceOp.SUM, group=self.group)
+            raise PeerFailure(int(f.item()))
+        return ordered_i64_to_u64(int(tau_cut))
+
+    def finish(self, job, k: int, s: int, m: int, name: str = "reads", failure: Optional[BaseException] = None):
+        """Collective: every rank calls it with its own job; every rank returns the same sketch.  `failure`: this rank
+        could not even feed its reads (the job is aborted, the other ranks are told, the exception is re-raised)."""
         P = self.world
         mark = self._mark or (lambda name: None)
+        if failure is not None:
+            if job:
+                _lib.load().ac_sketch_abort(job)
+            try:
+                self._tau_cut((1 << 64) - 1, False)
+            except PeerFailure:
+                pass
+            raise failure
         splits, tab = self.backend.local_table(job, self._tau_cut, P)
         mark("local_table")
         # -- step 2: sizes, then payload

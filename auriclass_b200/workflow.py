@@ -47,6 +47,16 @@ def engine(device: int = 0) -> MashGPU:
     return e
 
 
+def process_group_world() -> int:
+    """Ranks of the default torch.distributed process group when the caller set one up (one process per GPU, e.g. under
+    torchrun), else 1.  torch is not imported for the ordinary single-process CLI."""
+    import sys
+    dist = sys.modules.get("torch.distributed")
+    if dist is None or not dist.is_available() or not dist.is_initialized():
+        return 1
+    return int(dist.get_world_size())
+
+
 def add_tag(tag: str, lines: str) -> str:
     """Same rendering as auriclass/general.py:10-32."""
     full_tag = f"[{tag}]"
@@ -118,10 +128,20 @@ class MashGpuMethods:
                    "-k", str(self.kmer_size), "-s", str(self.sketch_size), *self.read_paths]
         command_list_of_str = [str(item) for item in command]
         logging.info(add_tag("mash sketch", " ".join(command_list_of_str) + "   [libauriclass_cuda]"))
-        eng = engine(self.device)
+        world = process_group_world()
+        if world > 1:
+            # one process per GPU: read blocks are dealt over the ranks, the counts merged by one hash-range exchange
+            # (BASELINE.json configs[2]); collective -- every rank runs this method and gets the same sketch
+            import torch
+            self._gpu_device = torch.cuda.current_device()
+        eng = engine(getattr(self, "_gpu_device", self.device))
         try:
-            sk = eng.sketch_reads([str(p) for p in self.read_paths], k=self.kmer_size, s=self.sketch_size,
-                                  m=self.minimal_kmer_coverage)
+            if world > 1:
+                sk = eng.sketch_reads_sharded([str(p) for p in self.read_paths], k=self.kmer_size, s=self.sketch_size,
+                                              m=self.minimal_kmer_coverage)
+            else:
+                sk = eng.sketch_reads([str(p) for p in self.read_paths], k=self.kmer_size, s=self.sketch_size,
+                                      m=self.minimal_kmer_coverage)
             stderr = sketch_reads_stderr(sk, self.query_sketch_path)
         except _lib.NoRecordsError:
             sk = None
@@ -180,7 +200,7 @@ class MashGpuMethods:
         command = ["mash", "dist", self.reference_sketch_path, self.query_sketch_path]
         command_list_of_str = [str(item) for item in command]
         logging.info(add_tag("mash dist", " ".join(command_list_of_str) + "   [libauriclass_cuda]"))
-        eng = engine(self.device)
+        eng = engine(getattr(self, "_gpu_device", self.device))
         refs = eng.load_references(self.reference_sketch_path)
         queries = getattr(self, "_gpu_query_sketches", None)
         if not queries or getattr(self, "_gpu_query_key", None) != str(self.query_sketch_path):
