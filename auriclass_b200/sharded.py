@@ -156,6 +156,7 @@ class ShardedSketcher:
             self.backend.share_torch_stream()
         self.device = self.backend.device
         self.last_exchange = {}
+        self.transport = "torch.distributed collectives: all-reduce MIN, all-to-all of (hash, count) ranges, all-gather of the owners' prefixes"
         self._mark = None   # optional callable(name): phase timing hook (tools/time_sharded.py)
 
     def close(self) -> None:

@@ -787,3 +787,112 @@ def test_fastq_long_reads_spanning_tiles_and_subtiles(engine):
         sk = engine.sketch_bytes([big], k=k, s=1000, m=m, chunk=3 << 20)
         assert_same_sketch(sk, oracle.sketch_parallel([big], k, 1000, m))
         assert sk.info["passes"] == 1
+
+
+# ------------------------------------------------------------------ round-2 additions
+def test_device_fed_default_size_segments_match_oracle(engine):
+    """The benchmarked configuration's shape: a device-resident feed that spans three DEFAULT-size (256 MiB) segments
+    (two full ones and a tail), count-table pass with tau updates between segments, against the oracle."""
+    import torch
+    n_reads = 1_750_000                                   # 563 MB of 4-line FASTQ
+    contigs = synth.genome(seed=20240001, scale=0.25)    # 3.1 Mb -> ~85x
+    text = synth.fastq_reads(contigs, n_reads, seed=77)
+    assert text.size > 2 * (256 << 20)
+    dev = torch.from_numpy(text).cuda()
+    job = engine._begin(27, 50000, 42, 3, AC_MODE_READS)
+    _lib.check(engine.lib.ac_sketch_feed_device(job, dev.data_ptr(), text.size, 0, 1))
+    from auriclass_b200.mash_gpu import StreamStats
+    sk = engine._end(job, "dev", 27, 50000, StreamStats())
+    ref = oracle.sketch_parallel([text], 27, 50000, 3)
+    assert sk.info["passes"] == 1
+    assert_same_sketch(sk, ref)
+    assert len(sk) == 50000
+    sk.free()
+    # the same bytes from host memory in 32 MiB feeds (the e2e arm of bench.py) give the same sketch
+    job = engine._begin(27, 50000, 42, 3, AC_MODE_READS)
+    step = 32 << 20
+    for off in range(0, text.size, step):
+        n = min(step, text.size - off)
+        _lib.check(engine.lib.ac_sketch_feed(job, text[off:].ctypes.data, n, 0, 1 if off + n >= text.size else 0))
+    sk = engine._end(job, "host", 27, 50000, StreamStats())
+    assert_same_sketch(sk, ref)
+    sk.free()
+
+
+def test_check_dependencies_passes_with_a_device_present():
+    """F2: the replacement of the `mash -h` probe (general.py:181-205) on a box that has the library and a B200."""
+    from auriclass_b200.workflow import check_dependencies
+    assert check_dependencies() is None
+    lib = _lib.load()
+    assert lib.ac_probe() == 0 and lib.ac_device_count() >= 1
+
+
+def test_sharded_public_entry_world1_and_workflow(engine, reads, tmp_path):
+    """MashGPU.sketch_reads_sharded (read-block cutter -> feeds -> exchange) over an NCCL group of one rank, with a
+    block size small enough that the two fixture files fall into ~40 blocks; then the same through the reference-shaped
+    workflow method, which switches to the sharded entry only when the group has more than one rank."""
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29733")
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        paths = [D + "NC_001416.1_1.fq.gz", D + "NC_001416.1_2.fq.gz"]
+        sk = engine.sketch_reads_sharded(paths, k=27, s=50000, m=3, block_bytes=64 << 10)
+        ref = oracle.sketch(reads, 27, 50000, 3)
+        assert_same_sketch(sk, ref)
+        assert sk.name == paths[0] and sk.stats.bytes_in == sum(len(r) for r in reads)
+        from auriclass_b200 import workflow
+        assert workflow.process_group_world() == 1
+        with pytest.raises(_lib.AcError):     # a rank whose blocks are not FASTQ: the error surfaces, nothing hangs
+            p = tmp_path / "bad.fq"
+            p.write_bytes(b"@r1\nACGT\nIIII\n" * 10)
+            engine.sketch_reads_sharded([str(p)], k=27, s=100, m=1)
+    finally:
+        for sh in engine._sharders.values():
+            sh.close()
+        engine._sharders.clear()
+        dist.destroy_process_group()
+
+
+from hypothesis import HealthCheck, given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+_base = st.sampled_from("ACGTACGTACGTACGTNnacgtRY-")
+
+
+@st.composite
+def _ragged_fastq(draw):
+    """Random reads (SURVEY.md section 4 'the new build must add'): N, lower case, IUPAC codes, records shorter than k,
+    CRLF or LF line ends, an optional missing final newline; a few reads are repeated so that m > 1 keeps something."""
+    n = draw(st.integers(1, 40))
+    eol = draw(st.sampled_from(["\n", "\r\n"]))
+    recs = []
+    for i in range(n):
+        L = draw(st.integers(1, 90))
+        seq = "".join(draw(st.lists(_base, min_size=L, max_size=L)))
+        rec = f"@r{i} x{eol}{seq}{eol}+{eol}{'I' * L}{eol}"
+        recs.extend([rec] * draw(st.sampled_from([1, 1, 2, 3])))
+    txt = "".join(recs)
+    if draw(st.booleans()):
+        txt = txt[: -len(eol)]
+    return txt.encode()
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@given(fq=_ragged_fastq(), k=st.sampled_from([5, 16, 21, 27, 32]), s=st.sampled_from([3, 50, 10000]), m=st.sampled_from([1, 2, 3]),
+       chunk=st.sampled_from([None, 7, 64, 1000]))
+def test_hypothesis_random_reads_match_oracle(engine, fq, k, s, m, chunk):
+    try:
+        ref = oracle.sketch([fq], k, s, m)
+    except ValueError:
+        ref = None
+    if ref is None or len(ref.hashes) == 0:
+        with pytest.raises(_lib.AcError):
+            engine.sketch_bytes([fq], k=k, s=s, m=m, chunk=chunk)
+        return
+    sk = engine.sketch_bytes([fq], k=k, s=s, m=m, chunk=chunk)
+    assert_same_sketch(sk, ref)
+    sk.free()
