@@ -15,7 +15,8 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("AURICLASS_CUDA_LIB", _HERE / "csrc" / "libauriclass_cuda.so"))
 
-AC_OK, AC_E_PARAM, AC_E_CUDA, AC_E_NOMEM, AC_E_NO_RECORDS, AC_E_FORMAT, AC_E_PARAM_MISMATCH, AC_E_STATE, AC_E_INTERNAL = range(9)
+(AC_OK, AC_E_PARAM, AC_E_CUDA, AC_E_NOMEM, AC_E_NO_RECORDS, AC_E_FORMAT, AC_E_PARAM_MISMATCH, AC_E_STATE, AC_E_INTERNAL,
+ AC_E_PEER) = range(10)
 AC_MODE_READS, AC_MODE_FASTA = 0, 1
 
 
@@ -38,6 +39,10 @@ class AcError(RuntimeError):
 
 class NoRecordsError(AcError):
     """Mash's `ERROR: Did not find fasta records in ...` (AC_E_NO_RECORDS)."""
+
+
+class PeerError(AcError):
+    """Sharded sketch: another rank of the exchange failed or did not answer (AC_E_PEER)."""
 
 
 # every symbol include/auriclass_cuda.h declares: name -> (restype, argtypes)
@@ -64,6 +69,14 @@ SIGNATURES = {
     "ac_job_table_export": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, _vp]),
     "ac_merge_counts": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_int, _u64p]),
     "ac_sketch_from_table": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(SketchInfo)]),
+    "ac_xchg_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(_vp)]),
+    "ac_xchg_ipc_handle": (C.c_int, [_vp, _vp]),
+    "ac_xchg_open_peers": (C.c_int, [_vp, _vp]),
+    "ac_xchg_set_peer_local": (C.c_int, [_vp, C.c_int, _vp]),
+    "ac_xchg_destroy": (None, [_vp]),
+    "ac_sketch_exchange_begin": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ac_sketch_exchange_merge": (C.c_int, [_vp]),
+    "ac_sketch_exchange_end": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(SketchInfo), C.POINTER(C.c_uint64 * 4)]),
     "ac_sketch_from_hashes": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.POINTER(_vp)]),
     "ac_sketch_size": (C.c_uint64, [_vp]),
     "ac_sketch_hashes": (C.c_int, [_vp, _vp, _vp]),
@@ -111,4 +124,6 @@ def check(rc: int) -> None:
     msg = load().ac_last_error().decode("utf-8", "replace")
     if rc == AC_E_NO_RECORDS:
         raise NoRecordsError(rc, msg)
+    if rc == AC_E_PEER:
+        raise PeerError(rc, msg)
     raise AcError(rc, msg)

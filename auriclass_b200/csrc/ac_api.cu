@@ -16,6 +16,7 @@
 
 #include "../../include/auriclass_cuda.h"
 #include "ac_common.cuh"
+#include "ac_xchg.cuh"
 
 using namespace ac;
 
@@ -1230,6 +1231,238 @@ extern "C" int ac_sketch_from_table(ac_ctx *c, const uint64_t *dev_hashes, const
         memset(info, 0, sizeof(*info));
         info->n_hashes = ns; info->max_hash = h.max_hash; info->sum_counts = h.sum_counts;
         info->genome_size = h.genome_size; info->coverage = h.coverage; info->hash_bits = use64 ? 64 : 32; info->passes = 1;
+    }
+    *out = sk;
+    return AC_OK;
+}
+
+// ------------------------------------------------------------------ peer-memory exchange (ac_xchg.cu)
+struct ac_xchg {
+    ac_ctx *ctx;
+    XLayout L;
+    XPeers peers;
+    bool opened[X_MAX];            // peers.base[r] came from cudaIpcOpenMemHandle
+    unsigned char *win;
+    XLocal *d_xl, *h_xl;
+    JobDev *h_jd2;                 // pinned copy of the job state read together with h_xl
+    unsigned long long epoch;
+    int phase;                     // 0 idle, 1 after _begin, 2 after _merge
+    ac_job *job;
+    int k, s, m, use64;
+    int local_rc;
+    char local_err[512];
+    unsigned long long counters[5];
+    SketchBuf skb;
+};
+
+extern "C" void ac_xchg_destroy(ac_xchg *x) {
+    if (!x) return;
+    cudaSetDevice(x->ctx->dev);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < X_MAX; r++) if (x->opened[r]) cudaIpcCloseMemHandle(x->peers.base[r]);
+    if (x->job) job_free(x->job);
+    if (x->skb.h || x->skb.c) sketch_buf_put(x->ctx, x->ctx->dev, x->skb);
+    cudaFree(x->win); cudaFree(x->d_xl); cudaFreeHost(x->h_xl); cudaFreeHost(x->h_jd2);
+    cudaGetLastError();
+    delete x;
+}
+
+extern "C" int ac_xchg_create(ac_ctx *c, int rank, int world, int sketch_cap, uint64_t inbox_entries, ac_xchg **out) {
+    if (!c || !out) return fail(AC_E_PARAM, "ac_xchg_create: NULL argument");
+    *out = nullptr;
+    if (world < 1 || world > X_MAX || rank < 0 || rank >= world) return fail(AC_E_PARAM, "ac_xchg_create: rank %d of %d (at most %d ranks)", rank, world, X_MAX);
+    if (sketch_cap < 1 || sketch_cap > (1 << 24)) return fail(AC_E_PARAM, "sketch capacity %d outside 1..2^24", sketch_cap);
+    if (c->active) return fail(AC_E_STATE, "ac_xchg_create while a sketch job is active");
+    CK(cudaSetDevice(c->dev));
+    int rc = alloc_select(c, (size_t)sketch_cap);
+    if (rc) return rc;
+    size_t cap_in = inbox_entries ? (size_t)inbox_entries : ((size_t)2 << 20);
+    cap_in = std::min(cap_in, c->sb.cap / (size_t)world) & ~(size_t)3;     // the staging area is the sort scratch
+    if (cap_in < 1024) return fail(AC_E_PARAM, "inbox capacity too small");
+    ac_xchg *x = new ac_xchg();
+    x->ctx = c;
+    x->L = xchg_layout((uint32_t)rank, (uint32_t)world, (uint32_t)cap_in, (uint32_t)sketch_cap);
+    cudaError_t e = cudaMalloc(&x->win, x->L.bytes);
+    if (e == cudaSuccess) e = cudaMemset(x->win, 0, (sizeof(XCtl) + 4095) & ~(size_t)4095);
+    if (e == cudaSuccess) e = cudaMalloc(&x->d_xl, sizeof(XLocal));
+    if (e == cudaSuccess) e = cudaMemset(x->d_xl, 0, sizeof(XLocal));
+    if (e == cudaSuccess) e = cudaHostAlloc(&x->h_xl, sizeof(XLocal), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc(&x->h_jd2, sizeof(JobDev), cudaHostAllocDefault);
+    if (e != cudaSuccess) { ac_xchg_destroy(x); return fail(e == cudaErrorMemoryAllocation ? AC_E_NOMEM : AC_E_CUDA, "exchange window of %zu bytes: %s", x->L.bytes, cudaGetErrorString(e)); }
+    x->peers.base[rank] = x->win;
+    // the final sketch is assembled straight into the buffers the ac_sketch will own; they are taken here and re-armed
+    // after every exchange, so no allocation (a potential device-wide synchronisation) sits between an exchange's launches
+    e = sketch_buf_get(c, (uint64_t)x->L.s_cap, &x->skb);
+    if (e != cudaSuccess) { ac_xchg_destroy(x); return fail(AC_E_NOMEM, "sketch buffers: %s", cudaGetErrorString(e)); }
+    *out = x;
+    return AC_OK;
+}
+
+extern "C" int ac_xchg_ipc_handle(ac_xchg *x, void *out64) {
+    if (!x || !out64) return fail(AC_E_PARAM, "ac_xchg_ipc_handle: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    CK(cudaSetDevice(x->ctx->dev));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, x->win));
+    memcpy(out64, &h, 64);
+    return AC_OK;
+}
+
+extern "C" int ac_xchg_open_peers(ac_xchg *x, const void *handles) {
+    if (!x || !handles) return fail(AC_E_PARAM, "ac_xchg_open_peers: NULL argument");
+    CK(cudaSetDevice(x->ctx->dev));
+    for (uint32_t r = 0; r < x->L.P; r++) {
+        if (r == x->L.rank || x->peers.base[r]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + 64 * (size_t)r, 64);
+        void *p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        x->peers.base[r] = (unsigned char *)p;
+        x->opened[r] = true;
+    }
+    return AC_OK;
+}
+
+extern "C" int ac_xchg_set_peer_local(ac_xchg *x, int r, ac_xchg *other) {
+    if (!x || !other || r < 0 || r >= (int)x->L.P) return fail(AC_E_PARAM, "ac_xchg_set_peer_local: bad argument");
+    if (other->L.P != x->L.P || other->L.cap_in != x->L.cap_in || other->L.s_cap != x->L.s_cap || (int)other->L.rank != r)
+        return fail(AC_E_PARAM_MISMATCH, "windows of one exchange must share world size and capacities");
+    if (other->ctx->dev != x->ctx->dev) {
+        CK(cudaSetDevice(x->ctx->dev));
+        cudaError_t e = cudaDeviceEnablePeerAccess(other->ctx->dev, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(AC_E_CUDA, "no peer access from device %d to %d: %s", x->ctx->dev, other->ctx->dev, cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    x->peers.base[r] = other->win;
+    return AC_OK;
+}
+
+extern "C" int ac_sketch_exchange_begin(ac_ctx *c, ac_job *j, ac_xchg *x, int k, int sketch_size, int min_copies, int failed) {
+    if (!c || !x || x->ctx != c) return fail(AC_E_PARAM, "ac_sketch_exchange_begin: bad argument");
+    if (x->phase != 0) return fail(AC_E_STATE, "an exchange is already in flight on this window");
+    if (j && j->ctx != c) return fail(AC_E_PARAM, "job belongs to another context");
+    if (sketch_size < 1 || (uint32_t)sketch_size > x->L.s_cap) return fail(AC_E_PARAM, "sketch size %d exceeds the window's capacity %u", sketch_size, x->L.s_cap);
+    for (uint32_t r = 0; r < x->L.P; r++) if (!x->peers.base[r]) return fail(AC_E_STATE, "window of rank %u has not been opened", r);
+    CK(cudaSetDevice(c->dev));
+    x->k = k; x->s = sketch_size; x->m = min_copies; x->use64 = k > 16;
+    x->local_rc = AC_OK; x->local_err[0] = 0; x->job = j;
+    memset(x->counters, 0, sizeof(x->counters));
+    int have_table = 0, table_mode = 0;
+    if (j && !failed) {
+        int rc = finish_local(j, true);
+        if (rc) { x->local_rc = rc; snprintf(x->local_err, sizeof(x->local_err), "%s", g_err); }
+        else {
+            const JobDev &h = *c->h_jd;
+            x->counters[0] = h.n_records; x->counters[1] = h.n_kept; x->counters[2] = h.n_bases - h.n_short_len;
+            x->counters[3] = h.n_kmers; x->counters[4] = h.cand_total;
+            have_table = 1; table_mode = j->table_pending ? 1 : 0;
+            j->ended_local = true;
+        }
+        cudaEventRecord(c->ev_job1, c->s_comp);      // ac_last_job_times: the local pass of a sharded job
+    } else if (!failed && !j) {
+        return fail(AC_E_PARAM, "ac_sketch_exchange_begin: no job (pass failed = 1 for a rank that could not feed its reads)");
+    } else {
+        x->local_rc = AC_E_STATE; snprintf(x->local_err, sizeof(x->local_err), "this rank failed before the exchange");
+    }
+    x->epoch++;
+    LaunchCtx lc{c->s_comp, &c->launches};
+    CountTable ctm = c->ct;
+    ctm.min_copies = (uint32_t)min_copies; ctm.bshift = 0;
+    launch_xchg_phase1(lc, x->peers, x->win, x->L, x->epoch, x->d_xl, c->d_jd, have_table, table_mode, x->local_rc ? 1ull : 0ull,
+                       c->ct, c->sb, ctm);
+    CK(cudaGetLastError());
+    x->phase = 1;
+    return AC_OK;
+}
+
+static int xchg_read(ac_xchg *x) {
+    ac_ctx *c = x->ctx;
+    CK(cudaMemcpyAsync(x->h_xl, x->d_xl, sizeof(XLocal), cudaMemcpyDeviceToHost, c->s_comp));
+    CK(cudaMemcpyAsync(x->h_jd2, c->d_jd, sizeof(JobDev), cudaMemcpyDeviceToHost, c->s_comp));
+    CK(cudaStreamSynchronize(c->s_comp));
+    return AC_OK;
+}
+
+extern "C" int ac_sketch_exchange_merge(ac_xchg *x) {
+    if (!x) return fail(AC_E_PARAM, "ac_sketch_exchange_merge: NULL argument");
+    if (x->phase != 1) return fail(AC_E_STATE, "call ac_sketch_exchange_begin first");
+    ac_ctx *c = x->ctx;
+    CK(cudaSetDevice(c->dev));
+    int rc = xchg_read(x);        // the one number the host needs: how many qualified keys this owner holds
+    if (rc) return rc;
+    LaunchCtx lc{c->s_comp, &c->launches};
+    uint64_t nq = 0;
+    const unsigned long long *keys = c->sb.tab_hash;
+    const uint32_t *cnts = c->sb.tab_cnt;
+    if (x->h_jd2->overflow) {
+        // the table could not take the entries (or one of them is the table's "empty" marker): sort-based merge
+        const uint64_t n = x->h_xl->n_in_total;
+        if (n > c->sb.cap) return fail(AC_E_NOMEM, "merge of %llu entries exceeds capacity %zu", (unsigned long long)n, c->sb.cap);
+        if (n) {
+            launch_xchg_compact_inbox(lc, x->win, x->L, x->d_xl, c->sb);
+            launch_merge_counts(lc, c->sb, c->d_jd, n, x->m);
+            CK(cudaGetLastError());
+            rc = read_jd(c);
+            if (rc) return rc;
+            nq = c->h_jd->n_qualified;
+        }
+        keys = c->sb.keys_a; cnts = c->sb.vals_a;
+    } else {
+        nq = x->h_jd2->n_qlist;
+        if (nq) {
+            CountTable ctm = c->ct;
+            ctm.min_copies = (uint32_t)x->m; ctm.bshift = 0;
+            launch_table_collect(lc, ctm, c->sb, c->d_jd, (uint32_t)nq);
+            launch_table_finish(lc, c->sb, c->d_jd, (uint32_t)nq, (uint32_t)nq, key_bits_for(x->h_jd2->max_hash), 0x7fffffff, 1);
+            CK(cudaGetLastError());
+        }
+    }
+    const uint32_t n_keep = (uint32_t)std::min<uint64_t>(nq, (uint64_t)x->s);
+    if (x->skb.h == nullptr || x->skb.cap < (uint64_t)x->s) return fail(AC_E_INTERNAL, "exchange window has no sketch buffers");
+    XHeader hdr;
+    hdr.v[0] = n_keep; hdr.v[1] = nq;
+    for (int i = 0; i < 5; i++) hdr.v[2 + i] = x->counters[i];
+    hdr.v[7] = x->local_rc ? (unsigned long long)XERR_PEER : 0ull;
+    launch_xchg_phase2(lc, x->peers, x->win, x->L, x->epoch, x->d_xl, c->d_jd, keys, cnts, n_keep, hdr, (uint32_t)x->s, x->skb.h, x->skb.c);
+    SelectBufs tmp = c->sb;
+    tmp.sk_hash = x->skb.h; tmp.sk_cnt = x->skb.c;
+    launch_finalize(lc, tmp, c->d_jd, x->use64);
+    CK(cudaGetLastError());
+    x->phase = 2;
+    return AC_OK;
+}
+
+extern "C" int ac_sketch_exchange_end(ac_xchg *x, ac_sketch **out, ac_sketch_info *info, uint64_t *stats /*[4] or NULL*/) {
+    if (!x || !out) return fail(AC_E_PARAM, "ac_sketch_exchange_end: NULL argument");
+    *out = nullptr;
+    if (x->phase != 2) return fail(AC_E_STATE, "call ac_sketch_exchange_merge first");
+    ac_ctx *c = x->ctx;
+    CK(cudaSetDevice(c->dev));
+    int rc = xchg_read(x);
+    x->phase = 0;
+    if (x->job) { job_free(x->job); x->job = nullptr; }
+    prof_collect(c);
+    if (rc) return rc;
+    const XLocal &xl = *x->h_xl;
+    const JobDev &h = *x->h_jd2;
+    if (stats) { stats[0] = xl.tau_cut; stats[1] = xl.n_in_total; stats[2] = xl.qualified_total; stats[3] = xl.err; }
+    if (x->local_rc) return fail(x->local_rc, "%s", x->local_err);
+    if (xl.err & XERR_TIMEOUT) return fail(AC_E_PEER, "exchange timed out waiting for another rank (err bits %u)", xl.err);
+    if (xl.err & XERR_OVERFLOW) return fail(AC_E_NOMEM, "a rank's share of the exchange exceeds the inbox capacity of %u entries (raise AC_XCHG_INBOX)", x->L.cap_in);
+    if (xl.err) return fail(AC_E_PEER, "sharded sketch aborted: another rank of the exchange failed (err bits %u)", xl.err);
+    if (xl.n_final == 0) return fail(AC_E_NO_RECORDS, "did not find sequence records (no hash reached the minimum copy number on any rank)");
+    ac_sketch *sk = new ac_sketch();
+    sk->ctx = c; sk->dev = c->dev; sk->n = xl.n_final; sk->k = x->k; sk->s = x->s; sk->hash_bits = x->use64 ? 64 : 32;
+    sk->length = (uint64_t)h.genome_size;
+    sk->d_hash = x->skb.h; sk->d_cnt = x->skb.c; sk->cap = x->skb.cap;
+    x->skb = SketchBuf{nullptr, nullptr, 0};       // the buffers now belong to the sketch; re-arm the window
+    if (sketch_buf_get(c, (uint64_t)x->L.s_cap, &x->skb) != cudaSuccess) { cudaGetLastError(); x->skb = SketchBuf{nullptr, nullptr, 0}; }
+    if (info) {
+        memset(info, 0, sizeof(*info));
+        info->n_hashes = xl.n_final; info->n_records = xl.counters[0]; info->n_kept = xl.counters[1]; info->total_len = xl.counters[2];
+        info->n_kmers = xl.counters[3]; info->n_candidates = xl.counters[4];
+        info->max_hash = h.max_hash; info->sum_counts = h.sum_counts; info->final_tau = xl.tau_cut;
+        info->genome_size = h.genome_size; info->coverage = h.coverage; info->hash_bits = x->use64 ? 64 : 32; info->passes = 1;
     }
     *out = sk;
     return AC_OK;

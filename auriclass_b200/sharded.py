@@ -57,12 +57,64 @@ def range_bounds(tau_cut: int, n_ranges: int) -> List[int]:
     return [(span * r + n_ranges - 1) // n_ranges for r in range(n_ranges)]
 
 
-class PeerFailure(_lib.AcError):
+class PeerFailure(_lib.PeerError):
     """Another rank of the group failed before the exchange (bad input in its read blocks, CUDA error, ...): raised
     on every rank at the first collective, so nobody is left waiting."""
 
     def __init__(self, n_failed: int):
-        super().__init__(_lib.AC_E_STATE, f"sharded sketch aborted: {n_failed} rank(s) of the group failed before the exchange")
+        super().__init__(_lib.AC_E_PEER, f"sharded sketch aborted: {n_failed} rank(s) of the group failed before the exchange")
+
+
+class PeerWindow:
+    """This rank's window of the NVLink peer-memory exchange (csrc/ac_xchg.cu, include/auriclass_cuda.h `ac_xchg_*`):
+    the hash-range exchange as kernels that store straight into the other GPUs' memory -- no collective library call
+    and two small host reads per isolate."""
+
+    def __init__(self, engine, rank: int, world: int, sketch_cap: int, inbox_entries: int = 0):
+        self.eng, self.lib, self.rank, self.world, self.sketch_cap = engine, engine.lib, rank, world, sketch_cap
+        h = C.c_void_p()
+        check(self.lib.ac_xchg_create(engine.ctx, rank, world, sketch_cap, inbox_entries, C.byref(h)))
+        self._h = h.value
+
+    def handle_bytes(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(self.lib.ac_xchg_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def open_peers(self, handles) -> None:
+        blob = b"".join(bytes(h) for h in handles)
+        assert len(blob) == 64 * self.world
+        check(self.lib.ac_xchg_open_peers(self._h, blob))
+
+    def set_peer_local(self, r: int, other: "PeerWindow") -> None:
+        check(self.lib.ac_xchg_set_peer_local(self._h, r, other._h))
+
+    def begin(self, job, k: int, s: int, m: int, failed: bool = False) -> None:
+        check(self.lib.ac_sketch_exchange_begin(self.eng.ctx, job or None, self._h, k, s, m, 1 if failed else 0))
+
+    def merge(self) -> None:
+        check(self.lib.ac_sketch_exchange_merge(self._h))
+
+    def end(self, name: str, k: int, s: int):
+        from .mash_gpu import GpuSketch
+        sk = C.c_void_p()
+        info = SketchInfo()
+        stats = (C.c_uint64 * 4)()
+        check(self.lib.ac_sketch_exchange_end(self._h, C.byref(sk), C.byref(info), C.byref(stats)))
+        out = GpuSketch(self.eng, sk.value, info, name, k, s)
+        self.last_stats = {"tau_cut": int(stats[0]), "received": int(stats[1]), "qualified_total": int(stats[2])}
+        return out
+
+    def close(self) -> None:
+        if self._h:
+            self.lib.ac_xchg_destroy(self._h)
+            self._h = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 @dataclass
@@ -151,15 +203,73 @@ class ShardedSketcher:
 
     def __init__(self, engine, rank: int, world: int, group: Optional[dist.ProcessGroup] = None, backend=None):
         self.rank, self.world, self.group = rank, world, group
+        self.engine = engine
         self.backend = backend if backend is not None else CudaTableBackend(engine)
-        if hasattr(self.backend, "share_torch_stream"):
-            self.backend.share_torch_stream()
         self.device = self.backend.device
         self.last_exchange = {}
-        self.transport = "torch.distributed collectives: all-reduce MIN, all-to-all of (hash, count) ranges, all-gather of the owners' prefixes"
         self._mark = None   # optional callable(name): phase timing hook (tools/time_sharded.py)
+        # Transport: kernels over NVLink peer memory when every rank sits on the same box and can open the others'
+        # windows (the product path on an NVSwitch box); else torch.distributed collectives (NCCL between boxes, gloo in
+        # the CPU tests of this host logic).  AC_XCHG=collectives forces the latter.
+        import os
+        self.peer: Optional[PeerWindow] = None
+        self._peer_ok = (isinstance(self.backend, CudaTableBackend) and world <= 16
+                         and os.environ.get("AC_XCHG", "peer") != "collectives")
+        self._set_transport()
+
+    TORCH_TRANSPORT = ("torch.distributed collectives: all-reduce MIN, all-to-all of (hash, count) ranges, "
+                       "all-gather of the owners' prefixes")
+    PEER_TRANSPORT = ("kernels over NVLink peer memory (CUDA IPC windows): tau post/min, scatter by owner into the owners' "
+                      "inboxes, owner merge, prefix push to every rank; no collective library call")
+
+    def _set_transport(self) -> None:
+        self.transport = self.PEER_TRANSPORT if self._peer_ok else self.TORCH_TRANSPORT
+        if not self._peer_ok and hasattr(self.backend, "share_torch_stream") and not self.backend.stream_shared:
+            self.backend.share_torch_stream()
+
+    def _peer_window(self, s: int) -> Optional[PeerWindow]:
+        """(Re)build the windows, collectively, when there is none yet or the sketch size outgrew it.  All ranks must
+        succeed, else all fall back to the collectives."""
+        if self.peer is not None and self.peer.sketch_cap >= s:
+            return self.peer
+        import os
+        import socket
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
+        win, handle, err = None, b"", ""
+        try:
+            win = PeerWindow(self.engine, self.rank, self.world, max(int(s), 65536), int(os.environ.get("AC_XCHG_INBOX", "0")))
+            handle = win.handle_bytes()
+        except Exception as e:   # noqa: BLE001 -- reported to the group below
+            err = repr(e)
+        infos = [None] * self.world
+        dist.all_gather_object(infos, (socket.gethostname(), handle, err), group=self.group)
+        ok = all(i[2] == "" for i in infos) and len({i[0] for i in infos}) == 1
+        if ok:
+            try:
+                win.open_peers([i[1] for i in infos])
+            except Exception as e:   # noqa: BLE001
+                err = repr(e)
+        oks = [None] * self.world
+        dist.all_gather_object(oks, ok and err == "", group=self.group)
+        if all(oks):
+            self.peer = win
+            return win
+        if win is not None:
+            win.close()
+        if self.rank == 0:
+            import logging
+            logging.warning("auriclass_b200: peer-memory exchange unavailable (%s); using torch.distributed collectives",
+                            "; ".join(i[2] for i in infos if i[2]) or err or "ranks on different hosts")
+        self._peer_ok = False
+        self._set_transport()
+        return None
 
     def close(self) -> None:
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
         if hasattr(self.backend, "unshare_stream"):
             self.backend.unshare_stream()
 
@@ -179,6 +289,24 @@ class ShardedSketcher:
         could not even feed its reads (the job is aborted, the other ranks are told, the exception is re-raised)."""
         P = self.world
         mark = self._mark or (lambda name: None)
+        win = self._peer_window(s) if self._peer_ok else None
+        if win is not None:
+            if failure is not None and job:
+                _lib.load().ac_sketch_abort(job)
+                job = None
+            try:
+                win.begin(job, k, s, m, failed=failure is not None)
+                mark("xchg_begin")
+                win.merge()
+                mark("xchg_merge")
+                sk = win.end(name, k, s)
+                mark("xchg_end")
+            except BaseException:
+                if failure is not None:
+                    raise failure
+                raise
+            self.last_exchange = dict(win.last_stats)
+            return sk
         if failure is not None:
             if job:
                 _lib.load().ac_sketch_abort(job)

@@ -46,7 +46,8 @@ enum {
     AC_E_FORMAT = 5,         /* input is not FASTA / 4-line FASTQ as the GPU parser requires */
     AC_E_PARAM_MISMATCH = 6, /* query and reference sketches disagree in k / hash width */
     AC_E_STATE = 7,          /* call sequence error (feed after end, ...) */
-    AC_E_INTERNAL = 8
+    AC_E_INTERNAL = 8,
+    AC_E_PEER = 9            /* sharded sketch: another rank of the exchange failed or did not answer */
 };
 
 /* ac_sketch_begin mode */
@@ -59,6 +60,7 @@ typedef struct ac_ctx ac_ctx;       /* device context: streams, scratch arenas  
 typedef struct ac_job ac_job;       /* a sketch under construction                          */
 typedef struct ac_sketch ac_sketch; /* finished bottom-s sketch, device resident            */
 typedef struct ac_refs ac_refs;     /* reference sketches of one .msh, device resident      */
+typedef struct ac_xchg ac_xchg;     /* this rank's window of the peer-memory exchange       */
 
 /* What `mash sketch` reports on stderr / stores in the .msh, plus parser counters. */
 typedef struct ac_sketch_info {
@@ -141,6 +143,32 @@ int ac_merge_counts(ac_ctx *ctx, uint64_t *dev_hashes, uint32_t *dev_counts, uin
  * sketch_size are kept). */
 int ac_sketch_from_table(ac_ctx *ctx, const uint64_t *dev_hashes, const uint32_t *dev_counts,
                          uint64_t n, int k, int sketch_size, ac_sketch **out, ac_sketch_info *info);
+
+/* ---- the same exchange as kernels over NVLink peer memory (one process per GPU of ONE box) ----------------
+ * Replaces, for the sharded FASTQ path, the single address space in which one `mash sketch -r -m` process counts
+ * all reads (auriclass/classes.py:576-596).  Every rank creates a window, publishes its 64-byte CUDA IPC handle
+ * (any transport: the host mirror uses torch.distributed's object all-gather, once), opens the others', and from
+ * then on an exchange is three calls that only launch kernels and read two small structs back:
+ *   ac_sketch_exchange_begin  ends the rank's local pass, posts its threshold to every rank, takes tau_cut = min,
+ *                             writes its table entries <= tau_cut into their owners' inboxes (hash-range owner
+ *                             r = floor(h P / (tau_cut + 1))) and adds up what arrives in its own inbox
+ *   ac_sketch_exchange_merge  sorts the owner's qualified keys, pushes the first <= s to every rank, assembles the
+ *                             ordered concatenation's first s entries and runs the estimates
+ *   ac_sketch_exchange_end    returns the sketch (identical on every rank) and the job-wide counters
+ * The calls are collective in the sense that every rank must make them, in the same order; a rank that failed
+ * before (bad input in its blocks) calls _begin with job = NULL, failed = 1 and every rank gets AC_E_PEER (the
+ * failing one its own error) -- nobody waits for more than 20 s for a rank that never shows up.
+ * inbox_entries: capacity per (sender, owner) pair, 0 = 2 Mi entries; sketch_cap: largest sketch size the window
+ * can carry.  ac_xchg_set_peer_local wires windows of the SAME process together (tests emulate ranks that way). */
+int ac_xchg_create(ac_ctx *ctx, int rank, int world, int sketch_cap, uint64_t inbox_entries, ac_xchg **out);
+int ac_xchg_ipc_handle(ac_xchg *x, void *out64);
+int ac_xchg_open_peers(ac_xchg *x, const void *handles /* [world][64], own slot ignored */);
+int ac_xchg_set_peer_local(ac_xchg *x, int rank, ac_xchg *other);
+void ac_xchg_destroy(ac_xchg *x);
+int ac_sketch_exchange_begin(ac_ctx *ctx, ac_job *job, ac_xchg *x, int k, int sketch_size, int min_copies, int failed);
+int ac_sketch_exchange_merge(ac_xchg *x);
+/* stats (may be NULL): tau_cut, entries received, qualified hashes over all owners, error bits */
+int ac_sketch_exchange_end(ac_xchg *x, ac_sketch **out, ac_sketch_info *info, uint64_t stats[4]);
 
 /* Build a device sketch from host hashes (a query .msh, or tests). */
 int ac_sketch_from_hashes(ac_ctx *ctx, const uint64_t *hashes, uint64_t n, int k, int sketch_size,

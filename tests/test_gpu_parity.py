@@ -896,3 +896,171 @@ def test_hypothesis_random_reads_match_oracle(engine, fq, k, s, m, chunk):
     sk = engine.sketch_bytes([fq], k=k, s=s, m=m, chunk=chunk)
     assert_same_sketch(sk, ref)
     sk.free()
+
+
+# ------------------------------------------------------------------ peer-memory exchange (csrc/ac_xchg.cu)
+def _peer_group(P, s_cap=65536, inbox=0):
+    """P ranks emulated in ONE process on one GPU: a context + window per rank, wired together directly
+    (ac_xchg_set_peer_local) -- the kernels, flags and epochs are those of the multi-process path, only the pointers
+    do not come from CUDA IPC."""
+    from auriclass_b200.mash_gpu import MashGPU
+    from auriclass_b200.sharded import PeerWindow
+    engines = [MashGPU(0) for _ in range(P)]
+    wins = [PeerWindow(e, r, P, s_cap, inbox) for r, e in enumerate(engines)]
+    for a in wins:
+        for r, b in enumerate(wins):
+            if a is not b:
+                a.set_peer_local(r, b)
+    return engines, wins
+
+
+def _close_group(engines, wins):
+    for w in wins:
+        w.close()
+    for e in engines:
+        e.close()
+
+
+def _feed_job(eng, bufs, k, s, m):
+    job = eng._begin(k, s, 42, m, AC_MODE_READS)
+    for i, b in enumerate(bufs):
+        a = np.frombuffer(b, np.uint8)
+        _lib.check(eng.lib.ac_sketch_feed(job, a.ctypes.data if a.size else None, a.size, i, 1))
+    return job
+
+
+def _exchange(engines, wins, shards, k, s, m):
+    """launch every rank's phase before any rank's next phase is waited for (one host thread plays all ranks)"""
+    jobs = [_feed_job(e, sh, k, s, m) for e, sh in zip(engines, shards)]
+    for w, j in zip(wins, jobs):
+        w.begin(j, k, s, m)
+    for w in wins:
+        w.merge()
+    return [w.end("reads", k, s) for w in wins]
+
+
+@pytest.mark.parametrize("P,k,s,m", [(2, 27, 1000, 3), (3, 27, 50000, 3), (4, 21, 2000, 2), (2, 16, 700, 1), (1, 27, 50000, 3)])
+def test_peer_exchange_emulated_ranks_small_tables(reads, P, k, s, m):
+    """sort-mode local tables (inputs below the speculation size); the same windows carry three exchanges in a row
+    (epochs), the second with an empty rank"""
+    engines, wins = _peer_group(P)
+    try:
+        fq = reads[0] + reads[1]
+        ref = oracle.sketch([fq], k, s, m)
+        for trial in range(3):
+            shards = [[x] for x in _split_fastq(fq, P)]
+            if trial == 1 and P > 1:
+                shards = [[b"".join(x[0] for x in shards)]] + [[b""] for _ in range(P - 1)]
+            sks = _exchange(engines, wins, shards, k, s, m)
+            for sk in sks:
+                h, c = sk.hashes()
+                assert np.array_equal(h, ref.hashes) and np.array_equal(c, ref.counts)
+                assert sk.genome_size == ref.genome_size and sk.coverage == ref.coverage
+                assert sk.info["n_kmers"] == ref.n_kmers and sk.info["n_kept"] == ref.n_kept
+                sk.free()
+            assert all(w.last_stats["tau_cut"] == wins[0].last_stats["tau_cut"] for w in wins)
+    finally:
+        _close_group(engines, wins)
+
+
+def test_peer_exchange_emulated_ranks_count_tables_and_dist():
+    """count-table local passes (speculative thresholds): 3 ranks x 8 MB shards; the merged sketch feeds dist"""
+    P, s, m = 3, 3000, 3
+    contigs = synth.genome(seed=43, scale=0.02)
+    fq = synth.fastq_reads(contigs, 75_000, seed=44).tobytes()
+    engines, wins = _peer_group(P)
+    try:
+        sks = _exchange(engines, wins, [[x] for x in _split_fastq(fq, P)], 27, s, m)
+        ref = oracle.sketch_parallel([fq], 27, s, m)
+        assert wins[0].last_stats["tau_cut"] < (1 << 60)
+        for sk in sks:
+            h, c = sk.hashes()
+            assert np.array_equal(h, ref.hashes) and np.array_equal(c, ref.counts)
+            assert sk.genome_size == ref.genome_size and sk.coverage == ref.coverage
+        fa = synth.fasta_bytes(contigs)
+        rsk = engines[0].sketch_bytes([fa], k=27, s=s, m=1, mode=AC_MODE_FASTA)
+        gr = engines[0].load_sketch_set([rsk.hashes()[0]], [rsk.length], 27, s, names=["g"])
+        row = engines[0].dist(gr, sks[0])[0]
+        d, p, cm, dn = oracle.dist(rsk.hashes()[0], ref.hashes, s, 27, rsk.length, int(ref.genome_size))
+        assert (row.common, row.denom) == (cm, dn) and rel_close(row.distance, d)
+        gr.free()
+    finally:
+        _close_group(engines, wins)
+
+
+def test_peer_exchange_failures_reach_every_rank():
+    """a rank with malformed reads, and a rank that never fed anything (failed = 1): every rank gets an error, the
+    failing rank its own; then the same windows complete a good exchange (nothing is left half-posted).  A share
+    beyond the inbox capacity is reported, not truncated."""
+    P, k, s, m = 3, 27, 500, 1
+    engines, wins = _peer_group(P, inbox=1024)
+    try:
+        contigs = synth.genome(seed=9, scale=0.0005)
+        fq = synth.fastq_reads(contigs, 300, seed=10).tobytes()
+        shards = _split_fastq(fq, P)
+        bad = b"@r1\nACGTACGTACGTACGTACGTACGTACGTACGT\nIIII\n" * 5       # no '+' line
+        jobs = [_feed_job(e, [sh], k, s, m) for e, sh in zip(engines, [shards[0], bad, shards[2]])]
+        for w, j in zip(wins, jobs):
+            w.begin(j, k, s, m)
+        for w in wins:
+            w.merge()
+        errs = []
+        for w in wins:
+            with pytest.raises(_lib.AcError) as e:
+                w.end("x", k, s)
+            errs.append(e.value.code)
+        assert errs[1] == _lib.AC_E_FORMAT and errs[0] == errs[2] == _lib.AC_E_PEER
+        jobs = [_feed_job(e, [sh], k, s, m) for e, sh in zip(engines, shards)]
+        for r, (w, j) in enumerate(zip(wins, jobs)):
+            if r == 2:
+                engines[2].lib.ac_sketch_abort(j)
+                w.begin(None, k, s, m, failed=True)
+            else:
+                w.begin(j, k, s, m)
+        for w in wins:
+            w.merge()
+        for w in wins:
+            with pytest.raises(_lib.AcError):
+                w.end("x", k, s)
+        sks = _exchange(engines, wins, [[x] for x in shards], k, s, m)
+        ref = oracle.sketch([fq], k, s, m)
+        for sk in sks:
+            assert np.array_equal(sk.hashes()[0], ref.hashes)
+        # overflow: ~45,000 distinct k-mers per rank against 1,024-entry inboxes
+        big = synth.fastq_reads(synth.genome(seed=11, scale=0.004), 1000, seed=12).tobytes()
+        jobs = [_feed_job(e, [sh], k, 60000, m) for e, sh in zip(engines, _split_fastq(big, P))]
+        for w, j in zip(wins, jobs):
+            w.begin(j, k, 60000, m)
+        for w in wins:
+            w.merge()
+        for w in wins:
+            with pytest.raises(_lib.AcError) as e:
+                w.end("x", k, 60000)
+            assert e.value.code in (_lib.AC_E_NOMEM, _lib.AC_E_PEER)
+    finally:
+        _close_group(engines, wins)
+
+
+def test_peer_exchange_through_the_sharder_world1(engine, reads):
+    """ShardedSketcher picks the peer transport on a CUDA backend: NCCL group of one rank, IPC handle exchange included"""
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29735")
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        sh = engine.sharder(None)
+        assert "peer memory" in sh.transport
+        sk = sh.finish(_feed_job(engine, reads, 27, 50000, 3), 27, 50000, 3, name="reads")
+        assert sh.peer is not None and len(sh.peer.handle_bytes()) == 64
+        assert_same_sketch(sk, oracle.sketch(reads, 27, 50000, 3))
+        sk2 = sh.finish(_feed_job(engine, reads[:1], 27, 100000, 2), 27, 100000, 2)     # outgrows the window: rebuilt
+        assert sh.peer.sketch_cap >= 100000
+        assert_same_sketch(sk2, oracle.sketch(reads[:1], 27, 100000, 2))
+    finally:
+        for s_ in engine._sharders.values():
+            s_.close()
+        engine._sharders.clear()
+        dist.destroy_process_group()
