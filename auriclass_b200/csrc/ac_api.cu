@@ -1272,10 +1272,11 @@ extern "C" int ac_xchg_create(ac_ctx *c, int rank, int world, int sketch_cap, ui
     *out = nullptr;
     if (world < 1 || world > X_MAX || rank < 0 || rank >= world) return fail(AC_E_PARAM, "ac_xchg_create: rank %d of %d (at most %d ranks)", rank, world, X_MAX);
     if (sketch_cap < 1 || sketch_cap > (1 << 24)) return fail(AC_E_PARAM, "sketch capacity %d outside 1..2^24", sketch_cap);
-    if (c->active) return fail(AC_E_STATE, "ac_xchg_create while a sketch job is active");
     CK(cudaSetDevice(c->dev));
-    int rc = alloc_select(c, (size_t)sketch_cap);
-    if (rc) return rc;
+    if (!c->sb_ok) {            // (with a job in flight the scratch exists already; the window brings its own sketch buffers)
+        int rc = alloc_select(c, (size_t)sketch_cap);
+        if (rc) return rc;
+    }
     size_t cap_in = inbox_entries ? (size_t)inbox_entries : ((size_t)2 << 20);
     cap_in = std::min(cap_in, c->sb.cap / (size_t)world) & ~(size_t)3;     // the staging area is the sort scratch
     if (cap_in < 1024) return fail(AC_E_PARAM, "inbox capacity too small");

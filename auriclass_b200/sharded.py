@@ -215,6 +215,8 @@ class ShardedSketcher:
         self.peer: Optional[PeerWindow] = None
         self._peer_ok = (isinstance(self.backend, CudaTableBackend) and world <= 16
                          and os.environ.get("AC_XCHG", "peer") != "collectives")
+        if self._peer_ok:
+            self._peer_window(65536)     # collective, like the construction of a sharder itself
         self._set_transport()
 
     TORCH_TRANSPORT = ("torch.distributed collectives: all-reduce MIN, all-to-all of (hash, count) ranges, "
@@ -225,7 +227,10 @@ class ShardedSketcher:
     def _set_transport(self) -> None:
         self.transport = self.PEER_TRANSPORT if self._peer_ok else self.TORCH_TRANSPORT
         if not self._peer_ok and hasattr(self.backend, "share_torch_stream") and not self.backend.stream_shared:
-            self.backend.share_torch_stream()
+            try:
+                self.backend.share_torch_stream()
+            except _lib.AcError:
+                pass    # a job is in flight on the library's own stream: the backend then synchronises the streams instead
 
     def _peer_window(self, s: int) -> Optional[PeerWindow]:
         """(Re)build the windows, collectively, when there is none yet or the sketch size outgrew it.  All ranks must
