@@ -22,6 +22,8 @@
 // with '@', its third line with '+', sequence and quality byte totals match, the
 // file ends on a record boundary); anything else raises AC_E_FORMAT -- the GPU
 // path never guesses.  Multi-line FASTA is handled in full (k-mers span lines).
+#include <stdlib.h>
+
 #include "ac_common.cuh"
 
 namespace ac {
@@ -463,6 +465,378 @@ __global__ void __launch_bounds__(K1_THREADS) k1q_emit(SegDesc sd, TileArrays ta
     write_out(s_out, s_off, total_emit, Z, out_off);
 }
 
+// ---------------------------------------------------------------- FASTQ, one pass: k1q_fused
+// The text is read ONCE (TMA bulk copy of a 16 KiB tile into shared memory) and the base stream written once.
+// What a tile emits depends on the line phase at its first byte and on its output offset; both are chained through
+// the tiles by decoupled look-back over ONE 64-bit status word per tile:
+//   aggregate  [63:62] = 1 | [61:60] newlines (mod 4) | 4 x 15 bits: bytes in lines of tile-local index 0..3 (mod 4)
+//   inclusive  [63:62] = 2 | [61:60] phase after the tile | [31:0] output offset after the tile
+// Aggregates compose ((nA, cA) then (nB, cB) = (nA + nB, cA[q] + cB[q - nA])), so a warp folds a window of 32
+// predecessors with one scan, a 64-bit rotate per lane (the four 16-bit class counts rotate as one register) and four
+// warp reductions.  The status words are cleared per segment by the launcher (no epoch tag fits beside 4 x 15 bits).
+// Output side: the tile's sequence lines ("runs": maximal stretches of emitted bytes, newline included) are listed in
+// shared memory as (output offset, source offset); every thread then PRODUCES aligned 16-byte vectors of the stream --
+// locates the run of its first byte by binary search, gathers 16 unaligned source bytes from the staged text (and 16
+// more from the next run when the vector straddles a record boundary), sanitises 4 bytes at a time and stores the
+// vector.  No lane idles on header / quality bytes, nothing is staged twice, and there is no per-thread byte loop.
+constexpr int FQ_THREADS = 256;
+constexpr int FQ_TILE = 16384;                        // raw text per tile
+constexpr int FQ_CHUNKS = FQ_TILE / K1_CHUNK;         // 512 chunks of 32 bytes: thread t owns chunks t and 256 + t
+constexpr int FQ_MAXRUNS = 1024;                      // runs listed per tile; beyond that (reads of < ~12 bytes) a byte-wise path
+constexpr int FQ_PAD = 32;                            // slack in front of / behind the staged text (unaligned gathers)
+constexpr uint32_t FQS_AGG = 1, FQS_INC = 2;
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int NT>
+__device__ __forceinline__ void block_excl_sum2(uint32_t &a, uint32_t &b, uint32_t *s_w /*[66]*/, uint32_t &tot_a, uint32_t &tot_b) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t ia = a, ib = b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t ta = __shfl_up_sync(FULL, ia, d), tb = __shfl_up_sync(FULL, ib, d);
+        if (lane >= d) { ia += ta; ib += tb; }
+    }
+    if (lane == 31) { s_w[warp] = ia; s_w[33 + warp] = ib; }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t xa = (lane < NT / 32) ? s_w[lane] : 0u, xb = (lane < NT / 32) ? s_w[33 + lane] : 0u, ya = xa, yb = xb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t ta = __shfl_up_sync(FULL, ya, d), tb = __shfl_up_sync(FULL, yb, d);
+            if (lane >= d) { ya += ta; yb += tb; }
+        }
+        s_w[lane] = ya - xa; s_w[33 + lane] = yb - xb;
+        if (lane == 31) { s_w[32] = ya; s_w[65] = yb; }
+    }
+    __syncthreads();
+    a = ia - a + s_w[warp]; b = ib - b + s_w[33 + warp];
+    tot_a = s_w[32]; tot_b = s_w[65];
+    __syncthreads();
+}
+
+struct FqShared {
+    __align__(128) uint8_t text[FQ_PAD + FQ_TILE + FQ_PAD];   // staged tile at text + FQ_PAD (TMA destination)
+    uint16_t run_out[FQ_MAXRUNS + 2], run_src[FQ_MAXRUNS + 2];
+    uint32_t w[66];
+    uint32_t acc[4];
+    uint32_t last_nl[16], last_em[16];   // per (row, warp): ballot of "last byte of the chunk is a newline / is emitted"
+    uint32_t phase_in, out_off, n_out, n_runs;
+    __align__(8) uint64_t bar;
+};
+
+// 16 source bytes starting at byte offset s of the staged text (s in [-FQ_PAD, FQ_TILE + FQ_PAD - 20]), as 4 words
+__device__ __forceinline__ void gather16(const uint8_t *text0, int s, uint32_t out[4]) {
+    const uint32_t addr = smem_addr(text0) + (uint32_t)s;
+    const uint32_t al = addr & ~3u, sh = (addr & 3u) * 8u;
+    uint32_t v[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[i]) : "r"(al + 4u * i));
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = __funnelshift_r(v[i], v[i + 1], sh);
+}
+
+__global__ void __launch_bounds__(FQ_THREADS, 5) k1q_fused(SegDesc sd, uint32_t n_tiles, u64 *__restrict__ status, JobDev *__restrict__ jd,
+                                                        const uint8_t *__restrict__ Zprev, uint8_t *__restrict__ Z) {
+    __shared__ FqShared sh;
+    const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t *text0 = sh.text + FQ_PAD;
+    const long long tile_lo = (long long)tile * FQ_TILE;
+    const long long seg_lo = sd.skip, seg_hi = (long long)sd.skip + sd.len, real_hi = seg_hi - (sd.append_nl ? 1 : 0);
+    const ParseState ps = jd->ps[sd.serial & 1u];
+
+    // ---- stage the tile: one TMA bulk copy (whole 16-byte vectors that hold text; the allocation granule covers them)
+    long long want = real_hi - tile_lo;
+    want = want < 0 ? 0 : (want > FQ_TILE ? FQ_TILE : want);
+    const uint32_t nbytes = ((uint32_t)want + 15u) & ~15u;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sh.bar)) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (nbytes) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&sh.bar)), "r"(nbytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_addr(text0)), "l"(sd.base + tile_lo), "r"(nbytes), "r"(smem_addr(&sh.bar)) : "memory");
+        }
+    }
+    if (tid < 4) sh.acc[tid] = 0;
+    if (tile == 0) copy_carry(sd, ps, Zprev, Z);
+    __syncthreads();
+    if (nbytes) {
+        uint32_t ok;
+        do {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(ok) : "r"(smem_addr(&sh.bar)), "r"(0u) : "memory");
+        } while (!ok);
+    }
+    if (sd.append_nl && seg_hi - 1 >= tile_lo && seg_hi - 1 < tile_lo + FQ_TILE && tid == 0) text0[seg_hi - 1 - tile_lo] = '\n';
+    const bool interior = tile_lo >= seg_lo && tile_lo + FQ_TILE <= real_hi;
+    if (!interior) __syncthreads();   // the patched byte
+
+    // ---- per chunk: newline mask, validity; rows r = 0, 1: chunk ch = 256 r + tid
+    uint32_t nl[2], valid[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const uint32_t ch = 256u * r + tid;
+        const uint4 x = reinterpret_cast<const uint4 *>(text0)[2 * ch], y = reinterpret_cast<const uint4 *>(text0)[2 * ch + 1];
+        const uint32_t w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+        uint32_t m = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) m |= (((newline_bits(w[j]) >> 7) * 0x01020408u) >> 24) << (4 * j);
+        uint32_t v = 0xffffffffu;
+        if (!interior) {
+            const long long pos = tile_lo + 32ll * ch;
+            const long long a = (seg_lo > pos ? seg_lo : pos) - pos, b = (seg_hi < pos + 32 ? seg_hi : pos + 32) - pos;
+            v = (b > a) ? bit_range((int)a, (int)b) : 0u;
+        }
+        valid[r] = v; nl[r] = m & v;
+    }
+    // newlines before each chunk inside the tile (both rows in one scan; row 1 follows row 0)
+    uint32_t L0a = __popc(nl[0]), L0b = __popc(nl[1]), tot_nl0, tot_nl1;
+    block_excl_sum2<FQ_THREADS>(L0a, L0b, sh.w, tot_nl0, tot_nl1);
+    const uint32_t L0[2] = {L0a, L0b + tot_nl0};
+    const uint32_t tile_nl = tot_nl0 + tot_nl1;
+    // bytes per tile-local line index (mod 4)
+    LineMasks lm[2];
+    {
+        uint32_t cnt[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            lm[r] = line_index_masks(nl[r]);
+#pragma unroll
+            for (int q = 0; q < 4; q++) cnt[q] += __popc(lines_of(lm[r], (q - L0[r]) & 3u, valid[r]));
+        }
+        uint32_t lo = cnt[0] | (cnt[1] << 16), hi = cnt[2] | (cnt[3] << 16);   // <= 64 * 32 per 16-bit field and warp
+        lo = __reduce_add_sync(FULL, lo); hi = __reduce_add_sync(FULL, hi);
+        if (lane == 0) {
+            atomicAdd(&sh.acc[0], lo & 0xFFFFu); atomicAdd(&sh.acc[1], lo >> 16);
+            atomicAdd(&sh.acc[2], hi & 0xFFFFu); atomicAdd(&sh.acc[3], hi >> 16);
+        }
+    }
+    // last-byte flags of every chunk (the next chunk's "previous byte" questions)
+    {
+        const uint32_t b0 = __ballot_sync(FULL, nl[0] >> 31), b1 = __ballot_sync(FULL, nl[1] >> 31);
+        if (lane == 0) { sh.last_nl[warp] = b0; sh.last_nl[8 + warp] = b1; }
+    }
+    __syncthreads();
+
+    // ---- look-back (warp 0): phase at the tile's first byte, output offset
+    if (warp == 0) {
+        const uint32_t c0 = sh.acc[0], c1 = sh.acc[1], c2 = sh.acc[2], c3 = sh.acc[3];
+        uint32_t P, O;
+        if (tile == 0) { P = ps.fq_phase & 3u; O = Z_CARRY; }
+        else {
+            if (lane == 0) {
+                const u64 agg = ((u64)FQS_AGG << 62) | ((u64)(tile_nl & 3u) << 60) | ((u64)c3 << 45) | ((u64)c2 << 30) | ((u64)c1 << 15) | (u64)c0;
+                st_status(&status[tile], agg);
+            }
+            uint32_t S_nl = 0, Sc[4] = {0, 0, 0, 0};     // composition of the tiles behind the current window, up to tile - 1
+            P = 0; O = 0;
+            for (long long top = (long long)tile - 1;; top -= 32) {
+                const long long idx = top - 31 + lane;    // ascending with the lane
+                u64 w = 0;
+                if (idx >= 0) { do { w = ld_status(&status[idx]); } while ((w >> 62) == 0); }
+                else if (idx == -1) w = ((u64)FQS_INC << 62) | ((u64)(ps.fq_phase & 3u) << 60) | (u64)Z_CARRY;   // virtual tile -1
+                const uint32_t flag = (uint32_t)(w >> 62);
+                const unsigned inc_mask = __ballot_sync(FULL, flag == FQS_INC);
+                const int F = inc_mask ? 31 - __clz(inc_mask) : -1;   // nearest inclusive prefix of this window
+                const bool use = (int)lane > F && flag == FQS_AGG;
+                const uint32_t my_nl = use ? (uint32_t)(w >> 60) & 3u : 0u;
+                uint32_t pre = my_nl;                                 // newlines of the used lanes before this one
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, pre, d); if ((int)lane >= d) pre += t; }
+                const uint32_t W_nl = __shfl_sync(FULL, pre, 31);
+                pre -= my_nl;
+                // class counts as 4 x 16 bits; rotating left by 16 * pre re-indexes them to the window's first used tile
+                u64 x = 0;
+                if (use) x = (w & 0x7FFFu) | (((w >> 15) & 0x7FFFu) << 16) | (((w >> 30) & 0x7FFFu) << 32) | (((w >> 45) & 0x7FFFu) << 48);
+                const uint32_t rot = 16u * (pre & 3u);
+                x = rot ? ((x << rot) | (x >> (64u - rot))) : x;
+                const uint32_t W0 = __reduce_add_sync(FULL, (uint32_t)x & 0xFFFFu), W1 = __reduce_add_sync(FULL, (uint32_t)(x >> 16) & 0xFFFFu);
+                const uint32_t W2 = __reduce_add_sync(FULL, (uint32_t)(x >> 32) & 0xFFFFu), W3 = __reduce_add_sync(FULL, (uint32_t)(x >> 48) & 0xFFFFu);
+                // window first, then what was folded before: c[q] = W[q] + S[q - W_nl]
+                const uint32_t Wc[4] = {W0, W1, W2, W3};
+                uint32_t N[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t from = (q - W_nl) & 3u;
+                    N[q] = Wc[q] + (from == 0 ? Sc[0] : from == 1 ? Sc[1] : from == 2 ? Sc[2] : Sc[3]);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) Sc[q] = N[q];
+                S_nl += W_nl;
+                if (inc_mask) {
+                    const u64 wi = __shfl_sync(FULL, w, F);
+                    const uint32_t Pi = (uint32_t)(wi >> 60) & 3u, Oi = (uint32_t)wi;
+                    const uint32_t seq = (1u - Pi) & 3u;      // tile-local line index of the sequence lines right behind that tile
+                    P = (Pi + S_nl) & 3u;
+                    O = Oi + (seq == 0 ? Sc[0] : seq == 1 ? Sc[1] : seq == 2 ? Sc[2] : Sc[3]);
+                    break;
+                }
+            }
+        }
+        const uint32_t seq = (1u - P) & 3u, qual = (3u - P) & 3u;
+        const uint32_t out_bytes = seq == 0 ? c0 : seq == 1 ? c1 : seq == 2 ? c2 : c3;
+        const uint32_t q_bytes = qual == 0 ? c0 : qual == 1 ? c1 : qual == 2 ? c2 : c3;
+        if (lane == 0) {
+            st_status(&status[tile], ((u64)FQS_INC << 62) | ((u64)((P + tile_nl) & 3u) << 60) | (u64)(O + out_bytes));
+            sh.phase_in = P; sh.out_off = O; sh.n_out = out_bytes;
+            if (out_bytes) atomicAdd(&jd->fq_seq_bytes, (u64)out_bytes);
+            if (q_bytes) atomicAdd(&jd->fq_qual_bytes, (u64)q_bytes);
+        }
+    }
+    __syncthreads();
+    const uint32_t P = sh.phase_in, O = sh.out_off, n_out = sh.n_out;
+
+    // ---- emitted bytes (sequence lines incl. their newline), format checks, run list
+    uint32_t emit[2], err = 0;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const uint32_t ch = 256u * r + tid;
+        const uint32_t ph = (P + L0[r]) & 3u;                     // phase of the line holding the chunk's first byte
+        emit[r] = lines_of(lm[r], (1u - ph) & 3u, valid[r]);
+        if (valid[r]) {
+            // is the byte in front of the chunk's first valid byte a newline?
+            bool prev_nl;
+            const long long pos = tile_lo + 32ll * ch;
+            const int vlo = __ffs(valid[r]) - 1;
+            if (pos + vlo == seg_lo) prev_nl = ps.at_line_start != 0;                 // first byte of the segment
+            else if (ch == 0) prev_nl = sd.base[tile_lo - 1] == '\n';                 // last byte of the previous tile
+            else if (lane > 0) prev_nl = (sh.last_nl[8 * r + warp] >> (lane - 1)) & 1u;
+            else if (warp > 0) prev_nl = sh.last_nl[8 * r + warp - 1] >> 31;
+            else prev_nl = sh.last_nl[7] >> 31;                                       // row 1 starts behind row 0's last chunk
+            const uint32_t ls = ((nl[r] << 1) | (prev_nl ? (1u << vlo) : 0u)) & valid[r];
+            if (ls) {
+                const uint32_t hdr = lines_of(lm[r], (0u - ph) & 3u, valid[r]), plus = lines_of(lm[r], (2u - ph) & 3u, valid[r]);
+                for (uint32_t x = ls & (hdr | plus); x; x &= x - 1) {
+                    const int b = __ffs(x) - 1;
+                    const uint8_t c = text0[32u * ch + b];
+                    if ((hdr >> b) & 1u) { if (c != '@') err |= FERR_FQ_HEADER; }
+                    else if (c != '+') err |= FERR_FQ_PLUS;
+                }
+            }
+        }
+    }
+    if (err) atomicOr(&jd->format_error, err);
+    {
+        const uint32_t b0 = __ballot_sync(FULL, emit[0] >> 31), b1 = __ballot_sync(FULL, emit[1] >> 31);
+        if (lane == 0) { sh.last_em[warp] = b0; sh.last_em[8 + warp] = b1; }
+    }
+    __syncthreads();
+    uint32_t starts[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        uint32_t prev_em;      // is the byte in front of the chunk emitted?  (a tile always starts a new run)
+        if (lane > 0) prev_em = (sh.last_em[8 * r + warp] >> (lane - 1)) & 1u;
+        else if (warp > 0) prev_em = sh.last_em[8 * r + warp - 1] >> 31;
+        else prev_em = r ? sh.last_em[7] >> 31 : 0u;
+        starts[r] = emit[r] & ~((emit[r] << 1) | prev_em);
+    }
+    // exclusive prefixes over the chunks in stream order: emitted bytes, run starts (rows packed 16 | 16)
+    uint32_t eb = __popc(emit[0]) | (__popc(emit[1]) << 16), rs = __popc(starts[0]) | (__popc(starts[1]) << 16), tot_e, tot_r;
+    block_excl_sum2<FQ_THREADS>(eb, rs, sh.w, tot_e, tot_r);
+    const uint32_t E[2] = {eb & 0xFFFFu, (eb >> 16) + (tot_e & 0xFFFFu)};
+    const uint32_t R[2] = {rs & 0xFFFFu, (rs >> 16) + (tot_r & 0xFFFFu)};
+    const uint32_t n_runs = (tot_r & 0xFFFFu) + (tot_r >> 16);
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        uint32_t k = R[r];
+        for (uint32_t x = starts[r]; x; x &= x - 1, k++) {
+            const int b = __ffs(x) - 1;
+            if (k < (uint32_t)FQ_MAXRUNS) {
+                sh.run_out[k] = (uint16_t)(E[r] + __popc(emit[r] & ((1u << b) - 1u)));
+                sh.run_src[k] = (uint16_t)(32u * (256u * r + tid) + b);
+            }
+        }
+    }
+    if (tid == 0) { sh.n_runs = n_runs; }
+    __syncthreads();
+
+    // ---- produce the stream: Z[O .. O + n_out)
+    if (n_out) {
+        if (n_runs <= (uint32_t)FQ_MAXRUNS) {
+            const uint32_t v_first = O >> 4, v_end = (O + n_out + 15u) >> 4;
+            for (uint32_t v = v_first + tid; v < v_end; v += FQ_THREADS) {
+                const int o0 = (int)(v * 16u) - (int)O;              // tile-local output offset of the vector's first byte (may be < 0)
+                const uint32_t key = o0 < 0 ? 0u : (uint32_t)o0;
+                uint32_t lo = 0, hi = n_runs;                        // last run with run_out <= key
+                while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sh.run_out[mid] <= key) lo = mid; else hi = mid; }
+                const int avail = (lo + 1 < n_runs ? (int)sh.run_out[lo + 1] : 0x7fffffff) - o0;   // bytes of the vector served by run lo
+                uint32_t wv[4];
+                gather16(text0, (int)sh.run_src[lo] + (o0 - (int)sh.run_out[lo]), wv);
+                if (avail < 16) {
+                    const int avail2 = (lo + 2 < n_runs ? (int)sh.run_out[lo + 2] : 0x7fffffff) - o0;
+                    if (avail2 >= 16) {
+                        uint32_t w2[4];
+                        gather16(text0, (int)sh.run_src[lo + 1] - avail, w2);    // byte i >= avail is byte i - avail of run lo + 1
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const int na = avail - 4 * i;                        // bytes of word i that still belong to run lo
+                            const uint32_t m = na >= 4 ? 0xffffffffu : (na <= 0 ? 0u : ((1u << (8 * na)) - 1u));
+                            wv[i] = (wv[i] & m) | (w2[i] & ~m);
+                        }
+                    } else {
+                        // three or more runs inside 16 bytes (reads of a few bases): byte by byte
+                        uint32_t rr = lo;
+#pragma unroll
+                        for (int wi = 0; wi < 4; wi++) {
+                            uint32_t acc = 0;
+#pragma unroll
+                            for (int bi = 0; bi < 4; bi++) {
+                                const int o = o0 + 4 * wi + bi;
+                                while (rr + 1 < n_runs && (int)sh.run_out[rr + 1] <= o) rr++;
+                                const int sidx = (int)sh.run_src[rr] + (o - (int)sh.run_out[rr]);
+                                const uint32_t byte = (sidx >= -FQ_PAD && sidx < FQ_TILE + FQ_PAD) ? text0[sidx] : 0u;
+                                acc |= byte << (8 * bi);
+                            }
+                            wv[wi] = acc;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) wv[i] = sanitise4_sep(wv[i]);
+                uint8_t *dst = Z + (size_t)v * 16u;
+                if (o0 >= 0 && (uint32_t)o0 + 16u <= n_out) {
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const int o = o0 + i;
+                        if (o >= 0 && (uint32_t)o < n_out) dst[i] = (uint8_t)(wv[i >> 2] >> (8 * (i & 3)));
+                    }
+                }
+            }
+        } else {
+            // more runs than the list holds: every thread writes its own emitted bytes, one at a time
+#pragma unroll 1
+            for (int r = 0; r < 2; r++) {
+                uint32_t d = O + E[r];
+                for (uint32_t x = emit[r]; x; x &= x - 1, d++) {
+                    const int b = __ffs(x) - 1;
+                    const uint32_t c = text0[32u * (256u * r + tid) + b];
+                    Z[d] = (uint8_t)(sanitise4_sep(c | 0x41414100u) & 0xFFu);
+                }
+            }
+        }
+    }
+
+    // ---- last tile: parser state for the next segment
+    if (tile + 1 == n_tiles && tid == 0) {
+        const uint32_t end_state = (P + tile_nl) & 3u;
+        uint32_t ends_nl = ps.at_line_start;
+        if (seg_hi > seg_lo) ends_nl = text0[seg_hi - 1 - tile_lo] == '\n';
+        ParseState nx;
+        nx.z_begin = Z_CARRY;
+        nx.n_zbuf = O + n_out;
+        if (sd.last_of_file) {
+            if (end_state != 0 || !ends_nl) atomicOr(&jd->format_error, (uint32_t)FERR_FQ_TRUNC);
+            nx.fq_phase = 0; nx.fa_type = 0; nx.at_line_start = 1;
+        } else {
+            nx.fq_phase = end_state; nx.fa_type = ps.fa_type; nx.at_line_start = ends_nl;
+        }
+        jd->ps[(sd.serial + 1u) & 1u] = nx;
+    }
+}
+
 // ---------------------------------------------------------------- FASTA
 struct FaThread {
     uint32_t emit;       // bytes emitted whatever the incoming line type (lines that start inside the chunk, and
@@ -598,7 +972,14 @@ __global__ void __launch_bounds__(K1_THREADS) k1_fasta(SegDesc sd, JobDev *__res
 void launch_parse_segment(const LaunchCtx &lc, const SegDesc &sd, unsigned long long *st1, unsigned long long *st2,
                           uint32_t *tile_arr, size_t tile_cap, JobDev *jd, const uint8_t *Zprev, uint8_t *Z, int part) {
     // sd.n_tiles >= 1 (an empty segment still threads the parser state through its single tile)
-    if (sd.fmt == FMT_FASTQ) {
+    static int fused = -1;
+    if (fused < 0) { const char *e = getenv("AC_K1_LEGACY"); fused = (e && *e && *e != '0') ? 0 : 1; }
+    if (sd.fmt == FMT_FASTQ && fused && part == PARSE_ALL) {
+        const uint32_t n_tiles = sd.len ? div_up((unsigned long long)sd.skip + sd.len, FQ_TILE) : 1u;
+        cudaMemsetAsync(st1, 0, (size_t)n_tiles * 8, lc.stream);      // status words of the look-back (no epoch tag in them)
+        k1q_fused<<<n_tiles, FQ_THREADS, 0, lc.stream>>>(sd, n_tiles, st1, jd, Zprev, Z);
+        ++*lc.launches;
+    } else if (sd.fmt == FMT_FASTQ) {
         TileArrays ta;
         ta.nl = tile_arr;
         for (int q = 0; q < 4; q++) ta.c[q] = tile_arr + (size_t)(q + 1) * tile_cap;

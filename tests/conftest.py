@@ -9,6 +9,12 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 # the reference's own tests use paths relative to the repository root ("tests/data/...")
 os.chdir(ROOT)
+# Tests that emulate several ranks of the peer-memory exchange inside ONE process on one GPU keep a kernel of "rank" A
+# spinning on a flag that a kernel of "rank" B sets.  CUDA multiplexes streams onto a few hardware queues (8 by default)
+# and two streams that share a queue run in order -- B's kernel would sit behind A's spin until it times out.  One queue
+# per stream (read when the CUDA context is created, so it has to be set before anything touches the GPU).  Real ranks
+# are separate processes on separate GPUs and need nothing of the kind.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 
 def pytest_configure(config):

@@ -49,7 +49,7 @@ def test_cli_report_tsv_is_byte_identical(kind, inputs, tmp_path):
     """Exactly the two CI invocations of test.yaml:58-78, then `cmp`."""
     report = tmp_path / "report.tsv"
     out = run_cli(["--expected_genome_size", "40000", "60000", "--output", str(report), "--log_file_path",
-                   str(tmp_path / "run.log"), "-V", "-r", "tests/data/ref_sketch.msh", "-c", "tests/data/clade_config.csv", *inputs])
+                   str(tmp_path / "run.log"), "--verbose", "-r", "tests/data/ref_sketch.msh", "-c", "tests/data/clade_config.csv", *inputs])
     assert out.returncode == 0, out.stderr[-3000:]
     golden = (DATA / f"reference_report_{kind}.tsv").read_bytes()
     assert report.read_bytes() == golden, (report.read_text(), golden.decode())
