@@ -675,8 +675,19 @@ static int run_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_o
         ProfScope ps(c, 1);
         CountTable off;
         memset(&off, 0, sizeof(off));
-        if (!launch_hash_segment(lc, j->k, Z, (uint32_t)(Z_CARRY + seg_len + 1), (int)((sd.serial + 1u) & 1u), c->d_jd, c->sb.keys_a,
-                                 c->sb.cap, j->seed, j->use64, j->table ? c->ct : off))
+        const uint32_t zmax = (uint32_t)(Z_CARRY + seg_len + 1);
+        const CountTable &ctu = j->table ? c->ct : off;
+        // The first segment of a count-table pass starts at the speculative threshold (1/32 of the hash space: ~8x the
+        // candidates of the later segments).  Its first third (text / 7 bytes of the stream: 4-line FASTQ is ~46 % bases)
+        // is hashed on its own and the threshold pulled down from what that slice qualified -- about 3x coverage of a
+        // 50x isolate, enough for s qualified hashes well below the speculative threshold -- before the rest runs.
+        const uint32_t head = (j->table && j->seg_serial == 0 && seg_len >= ((size_t)32 << 20)) ? hash_ctas_for((uint32_t)(seg_len / 7)) : 0u;
+        if (head) {
+            if (!launch_hash_segment(lc, j->k, Z, zmax, (int)((sd.serial + 1u) & 1u), c->d_jd, c->sb.keys_a, c->sb.cap, j->seed, j->use64, ctu, 0u, head))
+                return fail(AC_E_PARAM, "this build of libauriclass_cuda.so has no hash kernel for k = %d", j->k);
+            launch_table_tau_update(lc, c->ct, c->d_jd, j->s);
+        }
+        if (!launch_hash_segment(lc, j->k, Z, zmax, (int)((sd.serial + 1u) & 1u), c->d_jd, c->sb.keys_a, c->sb.cap, j->seed, j->use64, ctu, head))
             return fail(AC_E_PARAM, "this build of libauriclass_cuda.so has no hash kernel for k = %d", j->k);
     }
     j->seg_serial++;
@@ -1448,7 +1459,18 @@ extern "C" int ac_sketch_exchange_end(ac_xchg *x, ac_sketch **out, ac_sketch_inf
     const JobDev &h = *x->h_jd2;
     if (stats) { stats[0] = xl.tau_cut; stats[1] = xl.n_in_total; stats[2] = xl.qualified_total; stats[3] = xl.err; }
     if (x->local_rc) return fail(x->local_rc, "%s", x->local_err);
-    if (xl.err & XERR_TIMEOUT) return fail(AC_E_PEER, "exchange timed out waiting for another rank (err bits %u)", xl.err);
+    if (xl.err & XERR_TIMEOUT) {
+        // which wait gave up: the flags of this rank's window next to the epoch they should have reached
+        XCtl ctl;
+        memset(&ctl, 0, sizeof(ctl));
+        cudaMemcpy(&ctl, x->win, sizeof(ctl), cudaMemcpyDeviceToHost);
+        char fl[256];
+        int o = 0;
+        for (uint32_t r = 0; r < x->L.P && o < 200; r++)
+            o += snprintf(fl + o, sizeof(fl) - o, " r%u:%llu/%llu/%llu", r, ctl.tau_flag[r], ctl.in_flag[r], ctl.ga_flag[r]);
+        return fail(AC_E_PEER, "exchange %llu timed out waiting for another rank (err bits %u; tau/inbox/gather flags seen per rank:%s)",
+                    x->epoch, xl.err, fl);
+    }
     if (xl.err & XERR_OVERFLOW) return fail(AC_E_NOMEM, "a rank's share of the exchange exceeds the inbox capacity of %u entries (raise AC_XCHG_INBOX)", x->L.cap_in);
     if (xl.err) return fail(AC_E_PEER, "sharded sketch aborted: another rank of the exchange failed (err bits %u)", xl.err);
     if (xl.n_final == 0) return fail(AC_E_NO_RECORDS, "did not find sequence records (no hash reached the minimum copy number on any rank)");

@@ -128,7 +128,9 @@ size_t parse_tile_array_words(size_t max_tiles, size_t *tile_cap);
 // false: this build has no kernel for k (nothing launched)
 bool launch_hash_segment(const LaunchCtx &lc, int k, const uint8_t *Z, uint32_t max_zbuf, int ps_slot, JobDev *jd,
                          unsigned long long *cand, unsigned long long cand_cap, uint32_t seed, int use64,
-                         const CountTable &ct);
+                         const CountTable &ct, uint32_t cta0 = 0, uint32_t cta1 = 0xffffffffu);   // CTAs [cta0, cta1) of the segment's grid
+// CTAs of launch_hash_segment's grid that cover the first `zbytes` bytes of the base stream
+uint32_t hash_ctas_for(uint32_t zbytes);
 
 struct SelectBufs {
     unsigned long long *keys_a, *keys_b;  // candidate buffer (keys_a) and its ping-pong partner

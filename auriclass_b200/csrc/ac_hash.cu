@@ -154,7 +154,7 @@ template <int K, bool FLAT>
 __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t *__restrict__ Z, JobDev *__restrict__ jd,
                                                          unsigned long long *__restrict__ cand,
                                                          unsigned long long cand_cap, uint32_t seed, int ps_slot,
-                                                         const CountTable ct) {
+                                                         const CountTable ct, uint32_t cta0) {
     using Q = ackmer::QuadCfg<K>;
     constexpr int K2_MAXG = K2MaxGroups<K>::value;
     __shared__ __align__(128) uint8_t s_fwd_all[K2_WARPS][K2_TB + 64];  // base stream bytes of the sub-tile (TMA destination)
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t 
 
     const uint32_t n_zbuf = jd->ps[ps_slot].n_zbuf, z_begin = jd->ps[ps_slot].z_begin;
     const long long n_win = (long long)n_zbuf - K + 1;             // window starts 0 .. n_win-1 exist
-    const long long tile_start = ((long long)blockIdx.x * K2_WARPS + warp) * K2_WT;
+    const long long tile_start = ((long long)(cta0 + blockIdx.x) * K2_WARPS + warp) * K2_WT;
     uint32_t nk = 0, n_rec = 0, n_kept = 0, short_len = 0, n_bases = 0, n_emitted = 0;
 
     // a sub-tile is needed while it holds window starts; record-end positions p = start + K < n_zbuf
@@ -386,24 +386,29 @@ __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t 
 
 template <int K>
 void launch_k(const LaunchCtx &lc, const uint8_t *Z, uint32_t max_zbuf, int ps_slot, JobDev *jd, unsigned long long *cand,
-              unsigned long long cand_cap, uint32_t seed, const CountTable &ct) {
-    const unsigned grid = div_up(max_zbuf, K2_TILE);   // CTAs past the end of the stream leave at once (measured: no cost)
+              unsigned long long cand_cap, uint32_t seed, const CountTable &ct, uint32_t cta0, uint32_t cta1) {
+    unsigned grid = div_up(max_zbuf, K2_TILE);   // CTAs past the end of the stream leave at once (measured: no cost)
+    if (cta1 < grid) grid = cta1;
+    if (cta0 >= grid) return;
+    grid -= cta0;
 #if defined(AC_K2_BRANCHY)   // comparison builds: the branchy loop everywhere
-    k2_hash<K, false><<<grid, K2_THREADS, 0, lc.stream>>>(Z, jd, cand, cand_cap, seed, ps_slot, ct);
+    k2_hash<K, false><<<grid, K2_THREADS, 0, lc.stream>>>(Z, jd, cand, cand_cap, seed, ps_slot, ct, cta0);
 #else
-    if (ct.mask) k2_hash<K, true><<<grid, K2_THREADS, 0, lc.stream>>>(Z, jd, cand, cand_cap, seed, ps_slot, ct);
-    else k2_hash<K, false><<<grid, K2_THREADS, 0, lc.stream>>>(Z, jd, cand, cand_cap, seed, ps_slot, ct);
+    if (ct.mask) k2_hash<K, true><<<grid, K2_THREADS, 0, lc.stream>>>(Z, jd, cand, cand_cap, seed, ps_slot, ct, cta0);
+    else k2_hash<K, false><<<grid, K2_THREADS, 0, lc.stream>>>(Z, jd, cand, cand_cap, seed, ps_slot, ct, cta0);
 #endif
     ++*lc.launches;
 }
 
 }  // namespace
 
-#define AC_K_CASE(KK) case KK: launch_k<KK>(lc, Z, max_zbuf, ps_slot, jd, cand, cand_cap, seed, ct); break;
+uint32_t hash_ctas_for(uint32_t zbytes) { return div_up(zbytes, K2_TILE); }
+
+#define AC_K_CASE(KK) case KK: launch_k<KK>(lc, Z, max_zbuf, ps_slot, jd, cand, cand_cap, seed, ct, cta0, cta1); break;
 
 bool launch_hash_segment(const LaunchCtx &lc, int k, const uint8_t *Z, uint32_t max_zbuf, int ps_slot, JobDev *jd,
                          unsigned long long *cand, unsigned long long cand_cap, uint32_t seed, int use64,
-                         const CountTable &ct) {
+                         const CountTable &ct, uint32_t cta0, uint32_t cta1) {
     (void)use64;  // the hash width follows k (CandSink<(K > 16)>)
     switch (k) {
 #ifdef AC_ONLY_K27  // development builds: one instantiation, seconds to compile
