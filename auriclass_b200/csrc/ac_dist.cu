@@ -198,8 +198,14 @@ __device__ void d_finish_pair(u64 common, u64 denom, int k, u64 len_a, u64 len_b
 // Mash's capped merge (App. A.6) stops at the S-th distinct value and counts a twin of that value too, so:
 // common = twins whose rank (distinct values up to and including their A twin) is <= S, denom = min(S, distinct).
 // The walk ends as soon as the cap is reached or one list is exhausted -- the rest only adds to `distinct`.
-constexpr int P_WARPS = 4;      // pairs per CTA
-constexpr int P_BLOCK = 512;    // merged items per block and warp (2 x 4 KB of shared memory per warp)
+#ifndef AC_P_WARPS
+#define AC_P_WARPS 4
+#endif
+#ifndef AC_P_BLOCK
+#define AC_P_BLOCK 512
+#endif
+constexpr int P_WARPS = AC_P_WARPS;      // pairs per CTA
+constexpr int P_BLOCK = AC_P_BLOCK;      // merged items per block and warp (2 x 8 P_BLOCK bytes of shared memory per warp)
 
 struct PathPos { uint32_t i, j; };
 

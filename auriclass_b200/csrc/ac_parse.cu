@@ -23,6 +23,7 @@
 // file ends on a record boundary); anything else raises AC_E_FORMAT -- the GPU
 // path never guesses.  Multi-line FASTA is handled in full (k-mers span lines).
 #include <stdlib.h>
+#include <string.h>
 
 #include "ac_common.cuh"
 
@@ -479,9 +480,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1q_emit(SegDesc sd, TileArrays ta
 // locates the run of its first byte by binary search, gathers 16 unaligned source bytes from the staged text (and 16
 // more from the next run when the vector straddles a record boundary), sanitises 4 bytes at a time and stores the
 // vector.  No lane idles on header / quality bytes, nothing is staged twice, and there is no per-thread byte loop.
-constexpr int FQ_THREADS = 256;
-constexpr int FQ_TILE = 16384;                        // raw text per tile
-constexpr int FQ_CHUNKS = FQ_TILE / K1_CHUNK;         // 512 chunks of 32 bytes: thread t owns chunks t and 256 + t
+// NT threads per CTA, tile = 64 NT bytes (thread t owns the 32-byte chunks t and NT + t): 256 -> 16 KiB, 128 -> 8 KiB
 constexpr int FQ_MAXRUNS = 1024;                      // runs listed per tile; beyond that (reads of < ~12 bytes) a byte-wise path
 constexpr int FQ_PAD = 32;                            // slack in front of / behind the staged text (unaligned gathers)
 constexpr uint32_t FQS_AGG = 1, FQS_INC = 2;
@@ -515,8 +514,9 @@ __device__ __forceinline__ void block_excl_sum2(uint32_t &a, uint32_t &b, uint32
     __syncthreads();
 }
 
+template <int NT>
 struct FqShared {
-    __align__(128) uint8_t text[FQ_PAD + FQ_TILE + FQ_PAD];   // staged tile at text + FQ_PAD (TMA destination)
+    __align__(128) uint8_t text[FQ_PAD + 64 * NT + FQ_PAD];   // staged tile at text + FQ_PAD (TMA destination)
     uint16_t run_out[FQ_MAXRUNS + 2], run_src[FQ_MAXRUNS + 2];
     uint32_t w[66];
     uint32_t acc[4];
@@ -536,9 +536,11 @@ __device__ __forceinline__ void gather16(const uint8_t *text0, int s, uint32_t o
     for (int i = 0; i < 4; i++) out[i] = __funnelshift_r(v[i], v[i + 1], sh);
 }
 
-__global__ void __launch_bounds__(FQ_THREADS, 5) k1q_fused(SegDesc sd, uint32_t n_tiles, u64 *__restrict__ status, JobDev *__restrict__ jd,
-                                                        const uint8_t *__restrict__ Zprev, uint8_t *__restrict__ Z) {
-    __shared__ FqShared sh;
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k1q_fused(SegDesc sd, uint32_t n_tiles, u64 *__restrict__ status, JobDev *__restrict__ jd,
+                                                      const uint8_t *__restrict__ Zprev, uint8_t *__restrict__ Z) {
+    constexpr int FQ_THREADS = NT, FQ_TILE = 64 * NT, FQ_WARPS = NT / 32;
+    __shared__ FqShared<NT> sh;
     const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint8_t *text0 = sh.text + FQ_PAD;
     const long long tile_lo = (long long)tile * FQ_TILE;
@@ -576,7 +578,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 5) k1q_fused(SegDesc sd, uint32_t 
     uint32_t nl[2], valid[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-        const uint32_t ch = 256u * r + tid;
+        const uint32_t ch = (uint32_t)NT * r + tid;
         const uint4 x = reinterpret_cast<const uint4 *>(text0)[2 * ch], y = reinterpret_cast<const uint4 *>(text0)[2 * ch + 1];
         const uint32_t w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
         uint32_t m = 0;
@@ -598,14 +600,18 @@ __global__ void __launch_bounds__(FQ_THREADS, 5) k1q_fused(SegDesc sd, uint32_t 
     // bytes per tile-local line index (mod 4)
     LineMasks lm[2];
     {
-        uint32_t cnt[4] = {0, 0, 0, 0};
+        uint32_t packed = 0;                   // byte q: bytes of the thread's chunks in lines of tile-local index q (<= 64)
 #pragma unroll
         for (int r = 0; r < 2; r++) {
             lm[r] = line_index_masks(nl[r]);
-#pragma unroll
-            for (int q = 0; q < 4; q++) cnt[q] += __popc(lines_of(lm[r], (q - L0[r]) & 3u, valid[r]));
+            const uint32_t p0 = lm[r].p0, p1 = lm[r].p1, v = valid[r];
+            // chunk-local classes 0..3, one count per byte; chunk-local index i is tile-local index (i + L0) & 3:
+            // rotate the four bytes left by L0 bytes
+            const uint32_t c = __popc(~p0 & ~p1 & v) | (__popc(p0 & ~p1 & v) << 8) | (__popc(~p0 & p1 & v) << 16) | (__popc(p0 & p1 & v) << 24);
+            const uint32_t rot = 8u * (L0[r] & 3u);
+            packed += __funnelshift_l(c, c, rot);
         }
-        uint32_t lo = cnt[0] | (cnt[1] << 16), hi = cnt[2] | (cnt[3] << 16);   // <= 64 * 32 per 16-bit field and warp
+        uint32_t lo = (packed & 0xFFu) | ((packed & 0xFF00u) << 8), hi = ((packed >> 16) & 0xFFu) | ((packed >> 24) << 16);   // <= 64 * 32 per 16-bit field and warp
         lo = __reduce_add_sync(FULL, lo); hi = __reduce_add_sync(FULL, hi);
         if (lane == 0) {
             atomicAdd(&sh.acc[0], lo & 0xFFFFu); atomicAdd(&sh.acc[1], lo >> 16);
@@ -615,7 +621,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 5) k1q_fused(SegDesc sd, uint32_t 
     // last-byte flags of every chunk (the next chunk's "previous byte" questions)
     {
         const uint32_t b0 = __ballot_sync(FULL, nl[0] >> 31), b1 = __ballot_sync(FULL, nl[1] >> 31);
-        if (lane == 0) { sh.last_nl[warp] = b0; sh.last_nl[8 + warp] = b1; }
+        if (lane == 0) { sh.last_nl[warp] = b0; sh.last_nl[FQ_WARPS + warp] = b1; }
     }
     __syncthreads();
 
@@ -691,7 +697,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 5) k1q_fused(SegDesc sd, uint32_t 
     uint32_t emit[2], err = 0;
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-        const uint32_t ch = 256u * r + tid;
+        const uint32_t ch = (uint32_t)NT * r + tid;
         const uint32_t ph = (P + L0[r]) & 3u;                     // phase of the line holding the chunk's first byte
         emit[r] = lines_of(lm[r], (1u - ph) & 3u, valid[r]);
         if (valid[r]) {
@@ -701,9 +707,9 @@ __global__ void __launch_bounds__(FQ_THREADS, 5) k1q_fused(SegDesc sd, uint32_t 
             const int vlo = __ffs(valid[r]) - 1;
             if (pos + vlo == seg_lo) prev_nl = ps.at_line_start != 0;                 // first byte of the segment
             else if (ch == 0) prev_nl = sd.base[tile_lo - 1] == '\n';                 // last byte of the previous tile
-            else if (lane > 0) prev_nl = (sh.last_nl[8 * r + warp] >> (lane - 1)) & 1u;
-            else if (warp > 0) prev_nl = sh.last_nl[8 * r + warp - 1] >> 31;
-            else prev_nl = sh.last_nl[7] >> 31;                                       // row 1 starts behind row 0's last chunk
+            else if (lane > 0) prev_nl = (sh.last_nl[FQ_WARPS * r + warp] >> (lane - 1)) & 1u;
+            else if (warp > 0) prev_nl = sh.last_nl[FQ_WARPS * r + warp - 1] >> 31;
+            else prev_nl = sh.last_nl[FQ_WARPS - 1] >> 31;                                       // row 1 starts behind row 0's last chunk
             const uint32_t ls = ((nl[r] << 1) | (prev_nl ? (1u << vlo) : 0u)) & valid[r];
             if (ls) {
                 const uint32_t hdr = lines_of(lm[r], (0u - ph) & 3u, valid[r]), plus = lines_of(lm[r], (2u - ph) & 3u, valid[r]);
@@ -719,16 +725,16 @@ __global__ void __launch_bounds__(FQ_THREADS, 5) k1q_fused(SegDesc sd, uint32_t 
     if (err) atomicOr(&jd->format_error, err);
     {
         const uint32_t b0 = __ballot_sync(FULL, emit[0] >> 31), b1 = __ballot_sync(FULL, emit[1] >> 31);
-        if (lane == 0) { sh.last_em[warp] = b0; sh.last_em[8 + warp] = b1; }
+        if (lane == 0) { sh.last_em[warp] = b0; sh.last_em[FQ_WARPS + warp] = b1; }
     }
     __syncthreads();
     uint32_t starts[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
         uint32_t prev_em;      // is the byte in front of the chunk emitted?  (a tile always starts a new run)
-        if (lane > 0) prev_em = (sh.last_em[8 * r + warp] >> (lane - 1)) & 1u;
-        else if (warp > 0) prev_em = sh.last_em[8 * r + warp - 1] >> 31;
-        else prev_em = r ? sh.last_em[7] >> 31 : 0u;
+        if (lane > 0) prev_em = (sh.last_em[FQ_WARPS * r + warp] >> (lane - 1)) & 1u;
+        else if (warp > 0) prev_em = sh.last_em[FQ_WARPS * r + warp - 1] >> 31;
+        else prev_em = r ? sh.last_em[FQ_WARPS - 1] >> 31 : 0u;
         starts[r] = emit[r] & ~((emit[r] << 1) | prev_em);
     }
     // exclusive prefixes over the chunks in stream order: emitted bytes, run starts (rows packed 16 | 16)
@@ -744,7 +750,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 5) k1q_fused(SegDesc sd, uint32_t 
             const int b = __ffs(x) - 1;
             if (k < (uint32_t)FQ_MAXRUNS) {
                 sh.run_out[k] = (uint16_t)(E[r] + __popc(emit[r] & ((1u << b) - 1u)));
-                sh.run_src[k] = (uint16_t)(32u * (256u * r + tid) + b);
+                sh.run_src[k] = (uint16_t)(32u * ((uint32_t)NT * r + tid) + b);
             }
         }
     }
@@ -755,11 +761,15 @@ __global__ void __launch_bounds__(FQ_THREADS, 5) k1q_fused(SegDesc sd, uint32_t 
     if (n_out) {
         if (n_runs <= (uint32_t)FQ_MAXRUNS) {
             const uint32_t v_first = O >> 4, v_end = (O + n_out + 15u) >> 4;
+            const float runs_per_byte = (float)n_runs / (float)n_out;
             for (uint32_t v = v_first + tid; v < v_end; v += FQ_THREADS) {
                 const int o0 = (int)(v * 16u) - (int)O;              // tile-local output offset of the vector's first byte (may be < 0)
                 const uint32_t key = o0 < 0 ? 0u : (uint32_t)o0;
-                uint32_t lo = 0, hi = n_runs;                        // last run with run_out <= key
-                while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sh.run_out[mid] <= key) lo = mid; else hi = mid; }
+                // last run with run_out <= key: reads of one length make runs of one length, so the proportional guess is
+                // right or one off; the walk behind it is exact for any input
+                uint32_t lo = min(n_runs - 1u, (uint32_t)((float)key * runs_per_byte));
+                while (sh.run_out[lo] > key) lo--;
+                while (lo + 1 < n_runs && sh.run_out[lo + 1] <= key) lo++;
                 const int avail = (lo + 1 < n_runs ? (int)sh.run_out[lo + 1] : 0x7fffffff) - o0;   // bytes of the vector served by run lo
                 uint32_t wv[4];
                 gather16(text0, (int)sh.run_src[lo] + (o0 - (int)sh.run_out[lo]), wv);
@@ -812,7 +822,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 5) k1q_fused(SegDesc sd, uint32_t 
                 uint32_t d = O + E[r];
                 for (uint32_t x = emit[r]; x; x &= x - 1, d++) {
                     const int b = __ffs(x) - 1;
-                    const uint32_t c = text0[32u * (256u * r + tid) + b];
+                    const uint32_t c = text0[32u * ((uint32_t)NT * r + tid) + b];
                     Z[d] = (uint8_t)(sanitise4_sep(c | 0x41414100u) & 0xFFu);
                 }
             }
@@ -975,9 +985,20 @@ void launch_parse_segment(const LaunchCtx &lc, const SegDesc &sd, unsigned long 
     static int fused = -1;
     if (fused < 0) { const char *e = getenv("AC_K1_LEGACY"); fused = (e && *e && *e != '0') ? 0 : 1; }
     if (sd.fmt == FMT_FASTQ && fused && part == PARSE_ALL) {
-        const uint32_t n_tiles = sd.len ? div_up((unsigned long long)sd.skip + sd.len, FQ_TILE) : 1u;
+        static int nt = 0;
+        if (!nt) {
+            const char *e = getenv("AC_K1_NT");     // tuning: CTA size (tile = 64 x threads), "128", "256" or "256x6"
+            nt = e ? (!strcmp(e, "128") ? 128 : (!strcmp(e, "256x6") ? 2566 : 256)) : 256;
+            cudaFuncSetAttribute(k1q_fused<128, 10>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(k1q_fused<256, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(k1q_fused<256, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        }
+        const uint32_t tile_bytes = nt == 128 ? 8192u : 16384u;
+        const uint32_t n_tiles = sd.len ? div_up((unsigned long long)sd.skip + sd.len, tile_bytes) : 1u;
         cudaMemsetAsync(st1, 0, (size_t)n_tiles * 8, lc.stream);      // status words of the look-back (no epoch tag in them)
-        k1q_fused<<<n_tiles, FQ_THREADS, 0, lc.stream>>>(sd, n_tiles, st1, jd, Zprev, Z);
+        if (nt == 128) k1q_fused<128, 10><<<n_tiles, 128, 0, lc.stream>>>(sd, n_tiles, st1, jd, Zprev, Z);
+        else if (nt == 2566) k1q_fused<256, 6><<<n_tiles, 256, 0, lc.stream>>>(sd, n_tiles, st1, jd, Zprev, Z);
+        else k1q_fused<256, 5><<<n_tiles, 256, 0, lc.stream>>>(sd, n_tiles, st1, jd, Zprev, Z);
         ++*lc.launches;
     } else if (sd.fmt == FMT_FASTQ) {
         TileArrays ta;
