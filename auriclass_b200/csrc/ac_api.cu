@@ -87,8 +87,6 @@ struct ac_ctx {
     int ct_log2;               // log2(slots), AC_TABLE_LOG2
     uint8_t *d_Z[2];           // base stream of the segment in flight, ping-pong by segment parity
     unsigned long long *d_st1, *d_st2;  // K1 (FASTA) look-back status words (state, output offset), one per tile
-    uint32_t *d_tcnt;          // K1 (FASTQ) per-tile arrays (newline count -> phase, class byte counts -> output offset)
-    size_t tile_cap;
     uint32_t seg_epoch;        // serial of the last segment launched on this context (tags the status words)
     size_t max_tiles;
     JobDev *d_jd, *h_jd;
@@ -106,11 +104,6 @@ struct ac_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[3];
     cudaEvent_t ev_job0, ev_job1;
     cudaEvent_t ev_t0, ev_t1;  // ac_timer_start / ac_timer_stop
-    // FASTQ look-ahead: k1q_count + k1q_scan of the next segment run on s_aux beside the hash kernel of this one
-    cudaStream_t s_aux;
-    cudaEvent_t ev_emit;       // on s_comp: the last k1q_emit (or the start of the pass) is done -> the tile arrays are free
-    cudaEvent_t ev_pre;        // on s_aux: the pre-launched count + scan are done
-    bool lookahead;            // AC_LOOKAHEAD=1 turns it on
 };
 
 struct ac_job {
@@ -133,9 +126,6 @@ struct ac_job {
     size_t proc_piece, proc_off;      // first unprocessed byte
     size_t pending;                   // fed but unprocessed bytes
     bool first_of_stream;
-    bool pre_valid;                   // count + scan of the next segment were launched ahead (pre_sd, pre_key)
-    SegDesc pre_sd;
-    size_t pre_key[4];                // piece, offset, length, last_of_file of that segment
     double cand_bound;                // host-side bound on entries in the candidate buffer
     uint32_t n_table_host;
     unsigned long long tau_host;
@@ -331,25 +321,11 @@ static int create_impl(ac_ctx *c, int device) {
     c->max_tiles = c->seg_bytes / K1_TILE + 4;
     CK(cudaMalloc(&c->d_st1, c->max_tiles * 8)); CK(cudaMalloc(&c->d_st2, c->max_tiles * 8));
     CK(cudaMemset(c->d_st1, 0, c->max_tiles * 8)); CK(cudaMemset(c->d_st2, 0, c->max_tiles * 8));
-    {
-        const size_t words = parse_tile_array_words(c->max_tiles, &c->tile_cap);
-        CK(cudaMalloc(&c->d_tcnt, words * 4)); CK(cudaMemset(c->d_tcnt, 0, words * 4));
-    }
     c->seg_epoch = 0;
     CK(cudaMalloc(&c->d_jd, sizeof(JobDev)));
     CK(cudaHostAlloc(&c->h_jd, sizeof(JobDev), cudaHostAllocDefault));
     CK(cudaEventCreate(&c->ev_job0)); CK(cudaEventCreate(&c->ev_job1));
     CK(cudaEventCreate(&c->ev_t0)); CK(cudaEventCreate(&c->ev_t1));
-    {
-        int lo = 0, hi = 0;   // the short parser kernels go in front of the hash kernel's remaining CTAs
-        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CK(cudaStreamCreateWithPriority(&c->s_aux, cudaStreamNonBlocking, hi));
-        CK(cudaEventCreateWithFlags(&c->ev_emit, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&c->ev_pre, cudaEventDisableTiming));
-        // opt-in (AC_LOOKAHEAD=1): 4.44 -> 4.35 ms per C2 isolate in seven of eight runs, 4.96 ms in one
-        const char *la = getenv("AC_LOOKAHEAD");
-        c->lookahead = la && atoi(la) != 0;
-    }
     return AC_OK;
 }
 
@@ -362,14 +338,14 @@ extern "C" void ac_destroy(ac_ctx *c) {
     for (auto &b : c->sk_pool) { cudaFree(b.h); cudaFree(b.c); }
     c->sk_pool.clear();
     free_select(c);
-    cudaFree(c->d_Z[0]); cudaFree(c->d_Z[1]); cudaFree(c->d_st1); cudaFree(c->d_st2); cudaFree(c->d_tcnt); cudaFree(c->d_jd); cudaFreeHost(c->h_jd);
+    cudaFree(c->d_Z[0]); cudaFree(c->d_Z[1]); cudaFree(c->d_st1); cudaFree(c->d_st2); cudaFree(c->d_jd); cudaFreeHost(c->h_jd);
     for (auto &s : c->slabs) cudaFree(s.ptr);
     cudaFree(c->d_dist); cudaFree(c->d_p); cudaFree(c->d_common); cudaFree(c->d_denom); cudaFree(c->d_qmeta);
     cudaFreeHost(c->h_dist); cudaFreeHost(c->h_p); cudaFreeHost(c->h_common); cudaFreeHost(c->h_denom); cudaFreeHost(c->h_qmeta);
     for (auto ev : c->ev_pool) cudaEventDestroy(ev);
     for (int i = 0; i < 3; i++) for (auto &p : c->prof[i]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-    for (cudaEvent_t ev : {c->ev_job0, c->ev_job1, c->ev_emit, c->ev_pre, c->ev_t0, c->ev_t1}) if (ev) cudaEventDestroy(ev);
-    for (cudaStream_t st : {c->s_copy, c->s_own, c->s_aux}) if (st) cudaStreamDestroy(st);
+    for (cudaEvent_t ev : {c->ev_job0, c->ev_job1, c->ev_t0, c->ev_t1}) if (ev) cudaEventDestroy(ev);
+    for (cudaStream_t st : {c->s_copy, c->s_own}) if (st) cudaStreamDestroy(st);
     cudaGetLastError();
     delete c;
 }
@@ -378,7 +354,6 @@ extern "C" int ac_sync(ac_ctx *c) {
     if (!c) return fail(AC_E_PARAM, "ac_sync: ctx is NULL");
     CK(cudaSetDevice(c->dev));
     CK(cudaStreamSynchronize(c->s_copy));
-    CK(cudaStreamSynchronize(c->s_aux));
     CK(cudaStreamSynchronize(c->s_comp));
     return AC_OK;
 }
@@ -498,7 +473,7 @@ extern "C" int ac_sketch_begin(ac_ctx *c, int k, int sketch_size, uint32_t seed,
     j->use64 = k > 16 ? 1 : 0; j->seed = seed;
     j->cur_file = -1; j->file_open = false; j->cur_fmt = -1; j->tail_len = 0;
     j->pass_started = false; j->tau0 = 0; j->safe = false; j->table = false; j->passes = 0;
-    j->proc_piece = 0; j->proc_off = 0; j->pending = 0; j->first_of_stream = true; j->pre_valid = false;
+    j->proc_piece = 0; j->proc_off = 0; j->pending = 0; j->first_of_stream = true;
     j->cand_bound = 0; j->n_table_host = 0; j->tau_host = 0; j->bytes_done = 0; j->next_mark = 0; j->ended_local = false; j->table_pending = false;
     for (auto &s : c->slabs) s.used = 0;
     c->cur_slab = 0;
@@ -511,7 +486,6 @@ static void job_free(ac_job *j) {
     if (!j) return;
     ac_ctx *c = j->ctx;
     cudaStreamSynchronize(c->s_copy);
-    cudaStreamSynchronize(c->s_aux);   // a look-ahead launch of an aborted job may still be running
     cudaStreamSynchronize(c->s_comp);
     for (auto &p : j->pieces) if (p.ready) c->ev_pool.push_back(p.ready);
     if (c->active == j) c->active = nullptr;
@@ -580,8 +554,7 @@ static int start_pass(ac_job *j, unsigned long long tau0, bool safe) {
         c->ct.bshift = std::max(0, key_bits_for(tau0) - CT_BUCKET_BITS);
     }
     j->pass_started = true; j->tau0 = tau0; j->safe = safe; j->passes++;
-    j->proc_piece = 0; j->proc_off = 0; j->first_of_stream = true; j->pre_valid = false;
-    CK(cudaEventRecord(c->ev_emit, c->s_comp));   // look-ahead launches of this pass start after its set-up
+    j->proc_piece = 0; j->proc_off = 0; j->first_of_stream = true;
     j->cand_bound = 0; j->n_table_host = 0; j->tau_host = tau0; j->bytes_done = 0; j->next_mark = c->seg_bytes;
     return AC_OK;
 }
@@ -614,31 +587,6 @@ static int build_segdesc(ac_job *j, size_t pi, size_t off, size_t len, bool last
     return AC_OK;
 }
 
-// FASTQ look-ahead: the segment that run_segment will be called with next is already known (its bytes are there), so
-// its k1q_count + k1q_scan go to s_aux now, beside the hash kernel of the segment just launched.  They read the text,
-// the parser state left by the previous k1q_scan and the tail of the stream k1q_emit just wrote, and they write the
-// tile arrays, the other parser-state slot and the carry at the head of the other Z buffer -- all free once the
-// previous k1q_emit is done (ev_emit); the hash kernel touches none of them.  Not in profile mode (the per-kernel
-// times of ac_last_times want one stream).
-static int prelaunch_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_of_file) {
-    ac_ctx *c = j->ctx;
-    const Piece &p = j->pieces[pi];
-    if (!c->lookahead || c->profile || p.fmt != FMT_FASTQ || j->pre_valid) return AC_OK;
-    SegDesc sd;
-    int rc = build_segdesc(j, pi, off, len, last_of_file, &sd);
-    if (rc) return rc;
-    CK(cudaStreamWaitEvent(c->s_aux, c->ev_emit, 0));
-    if (p.ready) CK(cudaStreamWaitEvent(c->s_aux, p.ready, 0));
-    LaunchCtx lc{c->s_aux, &c->launches};
-    launch_parse_segment(lc, sd, c->d_st1, c->d_st2, c->d_tcnt, c->tile_cap, c->d_jd, c->d_Z[(sd.serial + 1u) & 1u],
-                         c->d_Z[sd.serial & 1u], PARSE_PRE);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(c->ev_pre, c->s_aux));
-    j->pre_sd = sd; j->pre_valid = true;
-    j->pre_key[0] = pi; j->pre_key[1] = off; j->pre_key[2] = len; j->pre_key[3] = last_of_file ? 1 : 0;
-    return AC_OK;
-}
-
 // run K1 + K2 over bytes [off, off+len) of piece pi (len <= SEG_BYTES)
 static int run_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_of_file) {
     ac_ctx *c = j->ctx;
@@ -654,23 +602,16 @@ static int run_segment(ac_job *j, size_t pi, size_t off, size_t len, bool last_o
         if (rc) return rc;
     }
     SegDesc sd;
-    int part = PARSE_ALL;
-    if (j->pre_valid) {   // count + scan are in flight on s_aux
-        if (j->pre_key[0] != pi || j->pre_key[1] != off || j->pre_key[2] != len || j->pre_key[3] != (last_of_file ? 1u : 0u))
-            return fail(AC_E_INTERNAL, "look-ahead launched another segment than the one that follows");
-        sd = j->pre_sd; j->pre_valid = false; part = PARSE_POST;
-        CK(cudaStreamWaitEvent(c->s_comp, c->ev_pre, 0));
-    } else {
-        if (p.ready) CK(cudaStreamWaitEvent(c->s_comp, p.ready, 0));
+    if (p.ready) CK(cudaStreamWaitEvent(c->s_comp, p.ready, 0));
+    {
         int rc = build_segdesc(j, pi, off, len, last_of_file, &sd);
         if (rc) return rc;
     }
     uint8_t *Z = c->d_Z[sd.serial & 1u];
     {
         ProfScope ps(c, 0);
-        launch_parse_segment(lc, sd, c->d_st1, c->d_st2, c->d_tcnt, c->tile_cap, c->d_jd, c->d_Z[(sd.serial + 1u) & 1u], Z, part);
+        launch_parse_segment(lc, sd, c->d_st1, c->d_st2, c->d_jd, c->d_Z[(sd.serial + 1u) & 1u], Z);
     }
-    if (c->lookahead && sd.fmt == FMT_FASTQ) CK(cudaEventRecord(c->ev_emit, c->s_comp));
     {
         ProfScope ps(c, 1);
         CountTable off;
@@ -765,16 +706,6 @@ static int pump(ac_job *j, bool all) {
         j->pending -= std::min(j->pending, len);
         j->proc_off += len;
         if (j->proc_off == piece_len && !open) { j->proc_piece++; j->proc_off = 0; }
-        // the segment the next turn of this loop will take, if any: start its count + scan beside the hash kernel
-        size_t usable2;
-        bool open2;
-        if (segment_available(j, all, &usable2, &open2)) {
-            size_t len2;
-            bool last2;
-            segment_extent(j, usable2, &len2, &last2);
-            rc = prelaunch_segment(j, j->proc_piece, j->proc_off, len2, last2);
-            if (rc) return rc;
-        }
     }
     return AC_OK;
 }

@@ -22,7 +22,10 @@ constexpr size_t SEG_SAFE_BYTES = 32u << 20;         // segment size when every 
 constexpr int K2_THREADS = AC_K2_THREADS;             // hash CTA: independent warps, no CTA barrier after the first
 constexpr int K2_WARPS = K2_THREADS / 32;
 constexpr int K2_W = 32;                             // window starts per lane and round
-constexpr int K2_WT = 2048;                          // window starts per hash WARP (its own sub-tile: 64 rounds of 32)
+#ifndef AC_K2_WT
+#define AC_K2_WT 2048
+#endif
+constexpr int K2_WT = AC_K2_WT;                       // window starts per hash WARP (its own sub-tile: 64 rounds of 32)
 constexpr int K2_TILE = K2_WARPS * K2_WT;            // window starts per hash CTA
 constexpr int K2_STAGE = 128;                        // candidate staging slots per hash warp (shared memory)
 constexpr int MAX_RANGES = 64;                       // hash ranges (= ranks) of the multi-GPU exchange
@@ -115,14 +118,9 @@ struct LaunchCtx {
 };
 
 // kernels' host-side launchers (defined in the .cu files)
-// part: PARSE_ALL, or the two halves of a FASTQ segment -- PARSE_PRE = k1q_count + k1q_scan (they only need the text,
-// the previous segment's parser state and its emitted stream: ac_api.cu runs them on a second stream beside the
-// previous segment's hash kernel), PARSE_POST = k1q_emit.  FASTA (one kernel) belongs to PARSE_POST.
-enum { PARSE_ALL = 0, PARSE_PRE = 1, PARSE_POST = 2 };
+// K1 over one segment: FASTQ -> k1q_fused (st1 = look-back status words, cleared here), FASTA -> k1_fasta (st1 / st2)
 void launch_parse_segment(const LaunchCtx &lc, const SegDesc &sd, unsigned long long *st1, unsigned long long *st2,
-                          uint32_t *tile_arr, size_t tile_cap, JobDev *jd, const uint8_t *Zprev, uint8_t *Z, int part);
-// words of the FASTQ per-tile arrays for segments of up to max_tiles tiles; *tile_cap = padded entries per array
-size_t parse_tile_array_words(size_t max_tiles, size_t *tile_cap);
+                          JobDev *jd, const uint8_t *Zprev, uint8_t *Z);
 // ps_slot: ParseState slot holding this segment's n_zbuf (= (serial + 1) & 1)
 // ct.mask != 0: candidates are inserted into the count table instead of being appended to cand
 // false: this build has no kernel for k (nothing launched)

@@ -165,7 +165,12 @@ __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t 
     __shared__ uint16_t s_groups_all[K2_WARPS][K2_MAXG];                // start positions of the groups of <= 32 consecutive valid windows
     __shared__ SinkShared s_sink_all[K2_WARPS];
     __shared__ __align__(8) uint64_t s_bar_all[K2_WARPS];
+#if defined(AC_K2_STAT64)
     __shared__ unsigned long long s_stat[6];  // kmers, records, kept, short_len, bases, candidates: summed over the CTA's warps
+#else
+    __shared__ uint32_t s_stat[6];            // kmers, records, kept, short_len, bases, candidates: summed over the CTA's warps
+                                              // (32 bits hold a CTA's totals; 64-bit shared atomics are a CAS loop)
+#endif
     __shared__ uint32_t s_done;               // warps that have finished; the last one adds s_stat to the job counters
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -198,7 +203,14 @@ __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t 
         mbar_wait(s_bar, 0);
 
         // ---- once per sub-tile: reverse complement + validity / separator bitmaps (chunk = 32 bytes)
+#if defined(AC_K2_RC_UNROLL)
+#pragma unroll
+        for (uint32_t it = 0; it < (K2_TB / 32 + 31) / 32; it++) {
+            const uint32_t c = lane + 32u * it;
+            if (c >= K2_TB / 32) break;
+#else
         for (uint32_t c = lane; c < K2_TB / 32; c += 32) {
+#endif
             uint32_t w[8];
             const uint4 a = reinterpret_cast<const uint4 *>(s_fwd)[2 * c], b4 = reinterpret_cast<const uint4 *>(s_fwd)[2 * c + 1];
             w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b4.x; w[5] = b4.y; w[6] = b4.z; w[7] = b4.w;
@@ -364,22 +376,27 @@ __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t 
     nk = __reduce_add_sync(FULL, nk); n_rec = __reduce_add_sync(FULL, n_rec); n_kept = __reduce_add_sync(FULL, n_kept);
     short_len = __reduce_add_sync(FULL, short_len); n_bases = __reduce_add_sync(FULL, n_bases);
     if (lane == 0) {
-        if (nk) atomicAdd(&s_stat[0], (unsigned long long)nk);
-        if (n_rec) atomicAdd(&s_stat[1], (unsigned long long)n_rec);
-        if (n_kept) atomicAdd(&s_stat[2], (unsigned long long)n_kept);
-        if (short_len) atomicAdd(&s_stat[3], (unsigned long long)short_len);
-        if (n_bases) atomicAdd(&s_stat[4], (unsigned long long)n_bases);
-        if (n_emitted) atomicAdd(&s_stat[5], (unsigned long long)n_emitted);
+#if defined(AC_K2_STAT64)
+        typedef unsigned long long stat_t;
+#else
+        typedef uint32_t stat_t;
+#endif
+        if (nk) atomicAdd(&s_stat[0], (stat_t)nk);
+        if (n_rec) atomicAdd(&s_stat[1], (stat_t)n_rec);
+        if (n_kept) atomicAdd(&s_stat[2], (stat_t)n_kept);
+        if (short_len) atomicAdd(&s_stat[3], (stat_t)short_len);
+        if (n_bases) atomicAdd(&s_stat[4], (stat_t)n_bases);
+        if (n_emitted) atomicAdd(&s_stat[5], (stat_t)n_emitted);
         __threadfence_block();
         if (atomicAdd(&s_done, 1u) == (uint32_t)K2_WARPS - 1u) {
             __threadfence_block();
-            const volatile unsigned long long *st = s_stat;
-            if (st[0]) atomicAdd(&jd->n_kmers, st[0]);
-            if (st[1]) atomicAdd(&jd->n_records, st[1]);
-            if (st[2]) atomicAdd(&jd->n_kept, st[2]);
-            if (st[3]) atomicAdd(&jd->n_short_len, st[3]);
-            if (st[4]) atomicAdd(&jd->n_bases, st[4]);
-            if (st[5]) atomicAdd(&jd->cand_total, st[5]);
+            const volatile stat_t *st = s_stat;
+            if (st[0]) atomicAdd(&jd->n_kmers, (unsigned long long)st[0]);
+            if (st[1]) atomicAdd(&jd->n_records, (unsigned long long)st[1]);
+            if (st[2]) atomicAdd(&jd->n_kept, (unsigned long long)st[2]);
+            if (st[3]) atomicAdd(&jd->n_short_len, (unsigned long long)st[3]);
+            if (st[4]) atomicAdd(&jd->n_bases, (unsigned long long)st[4]);
+            if (st[5]) atomicAdd(&jd->cand_total, (unsigned long long)st[5]);
         }
     }
 }

@@ -22,9 +22,6 @@
 // with '@', its third line with '+', sequence and quality byte totals match, the
 // file ends on a record boundary); anything else raises AC_E_FORMAT -- the GPU
 // path never guesses.  Multi-line FASTA is handled in full (k-mers span lines).
-#include <stdlib.h>
-#include <string.h>
-
 #include "ac_common.cuh"
 
 namespace ac {
@@ -271,17 +268,9 @@ struct TileShared {
     uint32_t tile, state_in, out_off;
 };
 
-// ---------------------------------------------------------------- FASTQ: count -> scan -> emit
-// What a tile emits depends on the line phase at its first byte (= newlines before it, mod 4) and on the
-// output offset (= sequence-line bytes before it).  Both are plain prefix sums over per-tile numbers, so
-// instead of chaining tiles inside one kernel (measured: with ~1200 short-lived tiles in flight the
-// look-back is the bottleneck) the FASTQ path runs three kernels per segment:
-//   k1q_count  per 8 KiB tile: newline count and the bytes in lines of local index 0..3 (mod 4)
-//   k1q_scan   one CTA: phase and output offset per tile, parser state for the next segment, carry
-//   k1q_emit   classify with the known phase, compact the sequence lines through shared memory,
-//              sanitise word-parallel, aligned 16-byte stores
-// Line classification is closed form per 32-byte chunk: two prefix-xor scans over the newline mask give
-// every byte's line index mod 4 (no per-line loop, no divergence).
+// ---------------------------------------------------------------- FASTQ line classification
+// Line classification is closed form per 32-byte chunk: two prefix-xor scans over the newline mask give every byte's
+// line index mod 4 (no per-line loop, no divergence).
 
 // exclusive prefix parity: bit i of the result = parity of popc(x & ((1 << i) - 1))
 __device__ __forceinline__ uint32_t prefix_xor_excl(uint32_t x) {
@@ -304,168 +293,6 @@ __device__ __forceinline__ uint32_t lines_of(const LineMasks &lm, uint32_t r, ui
     return ((r & 1u) ? lm.p0 : ~lm.p0) & ((r & 2u) ? lm.p1 : ~lm.p1) & valid;
 }
 
-// per-tile numbers, structure of arrays (k1q_scan reads them with 16-byte loads)
-struct TileArrays {          // passed by value
-    uint32_t *nl;            // [cap] newline count            -> (k1q_scan) phase of the line holding the tile's first byte
-    uint32_t *c[4];          // [cap] bytes in lines of tile-local index r (mod 4); c[0] -> (k1q_scan) output offset
-    uint32_t *flag;          // [1]   bit 31: set by the owner of the segment's last byte, bit 0: that byte is '\n'
-    uint2 *nlmask;           // [cap * K1_THREADS] per 32-byte chunk: .x newline mask, .y newlines before the chunk inside its tile;
-                             // k1q_count -> k1q_emit (8 B per 32 B of text through L2/HBM instead of recomputing the byte tests
-                             // and re-running the block scan)
-};
-
-__global__ void __launch_bounds__(K1_THREADS) k1q_count(SegDesc sd, TileArrays ta) {
-    __shared__ uint32_t s_w[33];
-    __shared__ uint32_t s_acc[4];
-    const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-    if (tid < 4) s_acc[tid] = 0;
-    uint32_t w[8];
-    ChunkMasks m;
-    load_chunk(sd, tile, tid, w, m);
-    uint32_t total_nl;
-    const uint32_t L0 = block_excl_sum<K1_THREADS>(__popc(m.nl), s_w, total_nl);  // syncs: s_acc is zeroed
-    ta.nlmask[(size_t)tile * K1_THREADS + tid] = make_uint2(m.nl, L0);
-    const LineMasks lm = line_index_masks(m.nl);
-    // bytes per tile-local line index: chunk-local index r belongs to tile-local index (r + L0) & 3
-    uint32_t cnt[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) cnt[q] = __popc(lines_of(lm, (q - L0) & 3u, m.valid));
-    uint32_t lo = cnt[0] | (cnt[1] << 16), hi = cnt[2] | (cnt[3] << 16);   // <= 32 * 32 per 16-bit field and warp
-    lo = __reduce_add_sync(FULL, lo); hi = __reduce_add_sync(FULL, hi);
-    if (lane == 0) {
-        atomicAdd(&s_acc[0], lo & 0xFFFFu); atomicAdd(&s_acc[1], lo >> 16);
-        atomicAdd(&s_acc[2], hi & 0xFFFFu); atomicAdd(&s_acc[3], hi >> 16);
-    }
-    if (tile + 1 == sd.n_tiles && m.valid) {  // (last tile only) the thread that owns the segment's last byte reports whether it is a newline
-        const int vhi = 32 - __clz(m.valid);
-        const long long pos0 = (long long)tile * K1_TILE + (long long)tid * K1_CHUNK;
-        if (pos0 + vhi == (long long)sd.skip + sd.len) *ta.flag = 0x80000000u | ((m.nl >> (vhi - 1)) & 1u);
-    }
-    __syncthreads();
-    if (tid == 0) ta.nl[tile] = total_nl;
-    if (tid == 0) { ta.c[0][tile] = s_acc[0]; ta.c[1][tile] = s_acc[1]; ta.c[2][tile] = s_acc[2]; ta.c[3][tile] = s_acc[3]; }
-}
-
-constexpr int SCAN_T = 1024;
-constexpr int SCAN_PER = 8;                        // tiles per thread and round: two 16-byte loads per array
-constexpr int SCAN_ROUND = SCAN_T * SCAN_PER;      // 8192 tiles = 64 MiB of text per round
-
-__global__ void __launch_bounds__(SCAN_T) k1q_scan(SegDesc sd, TileArrays ta, JobDev *__restrict__ jd,
-                                                   const uint8_t *__restrict__ Zprev, uint8_t *__restrict__ Z) {
-    __shared__ uint32_t s_w[33];
-    const uint32_t tid = threadIdx.x, n = sd.n_tiles;
-    const ParseState ps = jd->ps[sd.serial & 1u];
-    copy_carry(sd, ps, Zprev, Z);
-    uint32_t phase_run = ps.fq_phase, off_run = Z_CARRY;
-    unsigned long long qual_total = 0;
-    for (uint32_t r0 = 0; r0 < n; r0 += SCAN_ROUND) {   // the arrays are padded to a multiple of SCAN_ROUND
-        const uint32_t t0 = r0 + tid * SCAN_PER;
-        uint32_t nl[SCAN_PER], c[4][SCAN_PER];
-#pragma unroll
-        for (int v = 0; v < SCAN_PER / 4; v++) {
-            const uint4 x = reinterpret_cast<const uint4 *>(ta.nl + t0)[v];
-            nl[4 * v] = x.x; nl[4 * v + 1] = x.y; nl[4 * v + 2] = x.z; nl[4 * v + 3] = x.w;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const uint4 y = reinterpret_cast<const uint4 *>(ta.c[q] + t0)[v];
-                c[q][4 * v] = y.x; c[q][4 * v + 1] = y.y; c[q][4 * v + 2] = y.z; c[q][4 * v + 3] = y.w;
-            }
-        }
-        uint32_t local_nl = 0;
-#pragma unroll
-        for (int i = 0; i < SCAN_PER; i++) { if (t0 + i >= n) nl[i] = 0; local_nl += nl[i]; }
-        uint32_t tot_nl;
-        uint32_t run = block_excl_sum<SCAN_T>(local_nl, s_w, tot_nl) + phase_run;
-        uint32_t ph[SCAN_PER], outb[SCAN_PER], local_out = 0, local_q = 0;
-#pragma unroll
-        for (int i = 0; i < SCAN_PER; i++) {
-            ph[i] = run & 3u;
-            run += nl[i];
-            const uint32_t rs = (1u - ph[i]) & 3u, rq = (3u - ph[i]) & 3u;
-            uint32_t sb = 0, qb = 0;
-#pragma unroll
-            for (int q = 0; q < 4; q++) { if (q == (int)rs) sb = c[q][i]; if (q == (int)rq) qb = c[q][i]; }
-            if (t0 + i >= n) { sb = 0; qb = 0; }
-            outb[i] = sb; local_out += sb; local_q += qb;
-        }
-        uint32_t tot_out, tot_q;
-        uint32_t off = block_excl_sum<SCAN_T>(local_out, s_w, tot_out) + off_run;
-        block_excl_sum<SCAN_T>(local_q, s_w, tot_q);
-#pragma unroll
-        for (int i = 0; i < SCAN_PER; i++) { const uint32_t o = off; off += outb[i]; outb[i] = o; }
-#pragma unroll
-        for (int v = 0; v < SCAN_PER / 4; v++) {
-            reinterpret_cast<uint4 *>(ta.nl + t0)[v] = make_uint4(ph[4 * v], ph[4 * v + 1], ph[4 * v + 2], ph[4 * v + 3]);
-            reinterpret_cast<uint4 *>(ta.c[0] + t0)[v] = make_uint4(outb[4 * v], outb[4 * v + 1], outb[4 * v + 2], outb[4 * v + 3]);
-        }
-        phase_run += tot_nl; off_run += tot_out; qual_total += tot_q;
-    }
-    if (tid == 0) {
-        const uint32_t ends = *ta.flag;
-        *ta.flag = 0;
-        const uint32_t end_state = phase_run & 3u;
-        const uint32_t ends_nl = (ends & 0x80000000u) ? (ends & 1u) : ps.at_line_start;
-        jd->fq_seq_bytes += off_run - Z_CARRY;   // single writer: no other kernel of the job touches these
-        jd->fq_qual_bytes += qual_total;
-        ParseState nx;
-        nx.z_begin = Z_CARRY;
-        nx.n_zbuf = off_run;
-        if (sd.last_of_file) {
-            if (end_state != 0 || !ends_nl) atomicOr(&jd->format_error, (uint32_t)FERR_FQ_TRUNC);
-            nx.fq_phase = 0; nx.fa_type = 0; nx.at_line_start = 1;
-        } else {
-            nx.fq_phase = end_state; nx.fa_type = ps.fa_type; nx.at_line_start = ends_nl;
-        }
-        jd->ps[(sd.serial + 1u) & 1u] = nx;
-    }
-}
-
-__global__ void __launch_bounds__(K1_THREADS) k1q_emit(SegDesc sd, TileArrays ta, JobDev *__restrict__ jd, uint8_t *__restrict__ Z) {
-    __shared__ uint32_t s_w[33];
-    __shared__ __align__(16) uint32_t s_words[K1_THREADS * SW_STRIDE + 4];
-    __shared__ __align__(16) uint8_t s_out[K1_TILE + 32];
-    const uint32_t tile = blockIdx.x, tid = threadIdx.x;
-    const uint32_t tile_phase = ta.nl[tile], out_off = ta.c[0][tile];
-    const ParseState ps = jd->ps[sd.serial & 1u];
-    uint32_t w[8];
-    ChunkMasks m;
-    load_chunk_t<false>(sd, tile, tid, w, m);
-    const size_t chunk = (size_t)tile * K1_THREADS + tid;
-    const uint2 from_count = ta.nlmask[chunk];
-    m.nl = from_count.x;
-    const uint32_t L0 = from_count.y;
-#pragma unroll
-    for (int j = 0; j < 8; j++) s_words[tid * SW_STRIDE + j] = w[j];
-    // is the byte before this chunk's first valid byte a newline?  (the previous chunk's mask answers it)
-    uint32_t up = __shfl_up_sync(FULL, m.nl >> 31, 1);
-    if ((tid & 31u) == 0) up = chunk ? (ta.nlmask[chunk - 1].x >> 31) : 0u;
-    // (the segment's first byte sits in chunk 0 at bit sd.skip < 16: there the parser state of the previous segment decides)
-    const bool prev_nl = m.valid ? ((chunk == 0) ? (ps.at_line_start != 0) : (up != 0)) : false;
-    const LineMasks lm = line_index_masks(m.nl);
-    const uint32_t ph = (tile_phase + L0) & 3u;       // phase of the line holding the chunk's first byte
-    const uint32_t emit = lines_of(lm, (1u - ph) & 3u, m.valid);   // sequence lines, newline included (-> separator)
-    // format checks on the line starts of this chunk: headers start with '@', third lines with '+'
-    uint32_t err = 0;
-    const uint32_t ls = m.valid ? (((m.nl << 1) | (prev_nl ? (m.valid & (0u - m.valid)) : 0u)) & m.valid) : 0u;
-    if (ls) {
-        const uint32_t hdr = lines_of(lm, (0u - ph) & 3u, m.valid), plus = lines_of(lm, (2u - ph) & 3u, m.valid);
-        const uint8_t *bytes = reinterpret_cast<const uint8_t *>(s_words + tid * SW_STRIDE);
-        for (uint32_t x = ls & (hdr | plus); x; x &= x - 1) {
-            const int pos = __ffs(x) - 1;
-            const uint8_t ch = bytes[pos];
-            if ((hdr >> pos) & 1u) { if (ch != '@') err |= FERR_FQ_HEADER; }
-            else if (ch != '+') err |= FERR_FQ_PLUS;
-        }
-    }
-    if (err) atomicOr(&jd->format_error, err);
-    uint32_t total_emit;
-    const uint32_t E = block_excl_sum<K1_THREADS>(__popc(emit), s_w, total_emit);  // also orders s_words
-    const uint32_t s_off = out_off & 15u;
-    compact_runs(s_words, s_out, tid, emit, s_off + E);
-    __syncthreads();
-    write_out(s_out, s_off, total_emit, Z, out_off);
-}
-
 // ---------------------------------------------------------------- FASTQ, one pass: k1q_fused
 // The text is read ONCE (TMA bulk copy of a 16 KiB tile into shared memory) and the base stream written once.
 // What a tile emits depends on the line phase at its first byte and on its output offset; both are chained through
@@ -480,7 +307,15 @@ __global__ void __launch_bounds__(K1_THREADS) k1q_emit(SegDesc sd, TileArrays ta
 // locates the run of its first byte by binary search, gathers 16 unaligned source bytes from the staged text (and 16
 // more from the next run when the vector straddles a record boundary), sanitises 4 bytes at a time and stores the
 // vector.  No lane idles on header / quality bytes, nothing is staged twice, and there is no per-thread byte loop.
-// NT threads per CTA, tile = 64 NT bytes (thread t owns the 32-byte chunks t and NT + t): 256 -> 16 KiB, 128 -> 8 KiB
+// NT threads per CTA, tile = 64 NT bytes (thread t owns the 32-byte chunks t and NT + t).  Measured per C2 isolate:
+// 256 threads / 16 KiB at 6 CTAs per SM (40 registers) 1.30 ms, at 5 CTAs (44 registers) 1.40 ms, 128 threads / 8 KiB 1.55 ms.
+#ifndef AC_K1_NT
+#define AC_K1_NT 256
+#endif
+#ifndef AC_K1_MINB
+#define AC_K1_MINB 6
+#endif
+constexpr int FQ_NT = AC_K1_NT, FQ_MINB = AC_K1_MINB;
 constexpr int FQ_MAXRUNS = 1024;                      // runs listed per tile; beyond that (reads of < ~12 bytes) a byte-wise path
 constexpr int FQ_PAD = 32;                            // slack in front of / behind the staged text (unaligned gathers)
 constexpr uint32_t FQS_AGG = 1, FQS_INC = 2;
@@ -980,50 +815,21 @@ __global__ void __launch_bounds__(K1_THREADS) k1_fasta(SegDesc sd, JobDev *__res
 }  // namespace
 
 void launch_parse_segment(const LaunchCtx &lc, const SegDesc &sd, unsigned long long *st1, unsigned long long *st2,
-                          uint32_t *tile_arr, size_t tile_cap, JobDev *jd, const uint8_t *Zprev, uint8_t *Z, int part) {
+                          JobDev *jd, const uint8_t *Zprev, uint8_t *Z) {
     // sd.n_tiles >= 1 (an empty segment still threads the parser state through its single tile)
-    static int fused = -1;
-    if (fused < 0) { const char *e = getenv("AC_K1_LEGACY"); fused = (e && *e && *e != '0') ? 0 : 1; }
-    if (sd.fmt == FMT_FASTQ && fused && part == PARSE_ALL) {
-        static int nt = 0;
-        if (!nt) {
-            const char *e = getenv("AC_K1_NT");     // tuning: CTA size (tile = 64 x threads), "128", "256" or "256x6"
-            nt = e ? (!strcmp(e, "128") ? 128 : (!strcmp(e, "256x6") ? 2566 : 256)) : 256;
-            cudaFuncSetAttribute(k1q_fused<128, 10>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            cudaFuncSetAttribute(k1q_fused<256, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            cudaFuncSetAttribute(k1q_fused<256, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (sd.fmt == FMT_FASTQ) {
+        static bool carveout_set = false;
+        if (!carveout_set) {   // a preference, not a requirement: 6 CTAs x 21 KB of shared memory per SM
+            cudaFuncSetAttribute(k1q_fused<FQ_NT, FQ_MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            carveout_set = true;
         }
-        const uint32_t tile_bytes = nt == 128 ? 8192u : 16384u;
-        const uint32_t n_tiles = sd.len ? div_up((unsigned long long)sd.skip + sd.len, tile_bytes) : 1u;
+        const uint32_t n_tiles = sd.len ? div_up((unsigned long long)sd.skip + sd.len, 64u * FQ_NT) : 1u;
         cudaMemsetAsync(st1, 0, (size_t)n_tiles * 8, lc.stream);      // status words of the look-back (no epoch tag in them)
-        if (nt == 128) k1q_fused<128, 10><<<n_tiles, 128, 0, lc.stream>>>(sd, n_tiles, st1, jd, Zprev, Z);
-        else if (nt == 2566) k1q_fused<256, 6><<<n_tiles, 256, 0, lc.stream>>>(sd, n_tiles, st1, jd, Zprev, Z);
-        else k1q_fused<256, 5><<<n_tiles, 256, 0, lc.stream>>>(sd, n_tiles, st1, jd, Zprev, Z);
-        ++*lc.launches;
-    } else if (sd.fmt == FMT_FASTQ) {
-        TileArrays ta;
-        ta.nl = tile_arr;
-        for (int q = 0; q < 4; q++) ta.c[q] = tile_arr + (size_t)(q + 1) * tile_cap;
-        ta.flag = tile_arr + 5 * tile_cap;
-        ta.nlmask = reinterpret_cast<uint2 *>(tile_arr + 5 * tile_cap + 4);   // (8-byte aligned: cap is a multiple of 8192)
-        if (part != PARSE_POST) {
-            k1q_count<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, ta);
-            k1q_scan<<<1, SCAN_T, 0, lc.stream>>>(sd, ta, jd, Zprev, Z);
-            *lc.launches += 2;
-        }
-        if (part != PARSE_PRE) {
-            k1q_emit<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, ta, jd, Z);
-            ++*lc.launches;
-        }
-    } else if (part != PARSE_PRE) {
+        k1q_fused<FQ_NT, FQ_MINB><<<n_tiles, FQ_NT, 0, lc.stream>>>(sd, n_tiles, st1, jd, Zprev, Z);
+    } else {
         k1_fasta<<<sd.n_tiles, K1_THREADS, 0, lc.stream>>>(sd, jd, st1, st2, Zprev, Z);
-        ++*lc.launches;
     }
-}
-size_t parse_tile_array_words(size_t max_tiles, size_t *tile_cap) {
-    const size_t cap = ((max_tiles + SCAN_ROUND - 1) / SCAN_ROUND) * SCAN_ROUND;  // k1q_scan reads whole rounds
-    *tile_cap = cap;
-    return 5 * cap + 4 + 2 * cap * K1_THREADS;   // per-tile numbers, the flag word, (mask, count) per 32-byte chunk
+    ++*lc.launches;
 }
 
 }  // namespace ac

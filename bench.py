@@ -583,7 +583,6 @@ def main() -> None:
                                                           f"({sharded.transport})",
                 "n_kmers_per_gpu": int(n_kmers), "n_candidates_per_gpu": int(n_cand), "sketch_hashes": int(n_hashes),
                 "passes": int(passes),
-                "lookahead": os.environ.get("AC_LOOKAHEAD", "0") not in ("", "0"),   # k1q_count/scan of segment i+1 beside K2 of segment i
             },
             "parity": parity,
             "e2e": {"value": (bases_total if args.config == "c3" else world * bases_rank) / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s",

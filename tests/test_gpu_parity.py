@@ -720,26 +720,24 @@ def test_flat_loop_redo_list_overflow(engine, k):
     assert sk.info["passes"] == 1
 
 
-def test_fastq_lookahead_on_a_second_stream(reads):
-    """AC_LOOKAHEAD=1: k1q_count + k1q_scan of segment i+1 run on a second stream beside the hash kernel of segment i.
-    Many small segments (AC_SEG_MB=1), device-resident and host-fed, two files merged, a pass that is repeated after
-    a failed speculation, and the tau = max path: every sketch must equal the oracle's."""
+def test_fastq_many_small_segments_device_and_host_fed(reads):
+    """Many small segments (AC_SEG_MB=1: the parser state, the stream carry and the look-back status words are handed from
+    segment to segment 38 times), device-resident and host-fed, two files merged, a pass that is repeated after a failed
+    speculation, and the tau = max path: every sketch must equal the oracle's."""
     import os
     import torch
     from auriclass_b200.mash_gpu import MashGPU, StreamStats
     os.environ["AC_SEG_MB"] = "1"
-    os.environ["AC_LOOKAHEAD"] = "1"
     try:
         eng = MashGPU(0)
     finally:
         del os.environ["AC_SEG_MB"]
-        del os.environ["AC_LOOKAHEAD"]
     try:
         contigs = synth.genome(seed=17, scale=0.01)
         fq = synth.fastq_reads(contigs, 120_000, seed=18).tobytes()   # ~38 MB, 38 segments
         ref = oracle.sketch_parallel([fq], 27, 2000, 3)
         t = torch.frombuffer(bytearray(fq), dtype=torch.uint8).cuda()
-        for _ in range(2):   # device-resident feed: every segment but the first is launched ahead
+        for _ in range(2):   # device-resident feed
             job = eng._begin(27, 2000, 42, 3, AC_MODE_READS)
             _lib.check(eng.lib.ac_sketch_feed_device(job, t.data_ptr(), t.numel(), 0, 1))
             assert_same_sketch(eng._end(job, "dev", 27, 2000, StreamStats()), ref)

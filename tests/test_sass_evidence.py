@@ -78,3 +78,31 @@ def test_k2_does_not_spill_at_the_production_k():
             regs = int(re.search(r"Used (\d+) registers", b).group(1))
             assert regs <= 64, regs   # 8 CTAs of 128 threads per SM
     assert seen == 2
+
+
+def test_k1_fastq_parser_stages_its_tile_with_tma_and_fits_six_ctas():
+    """north_star (a): the record parser's text goes through TMA / shared memory -- k1q_fused brings its 16 KiB tile in
+    with one bulk copy on an mbarrier; 40 registers x 256 threads and ~21 KB of shared memory keep 6 CTAs on an SM."""
+    obj = ROOT / "auriclass_b200" / "csrc" / "ac_parse.o"
+    if not obj.exists():
+        import __graft_entry__ as g
+        g.build()
+    out = subprocess.run(["cuobjdump", "-sass", str(obj)], capture_output=True, text=True, check=True).stdout
+    body, on = [], False
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            on = "k1q_fused" in m.group(1)
+        elif on:
+            body.append(line)
+    assert body, "k1q_fused not found in ac_parse.o"
+    txt = "\n".join(body)
+    assert "UBLKCP" in txt and "SYNCS" in txt
+    assert "REDUX" in txt          # the look-back folds 32 predecessors with warp reductions
+    log = ROOT / "auriclass_b200" / "csrc" / "ac_parse.ptxas.log"
+    if log.exists():
+        for b in re.split(r"ptxas info\s+: Compiling entry function ", log.read_text()):
+            if "k1q_fused" in b[:200]:
+                regs = int(re.search(r"Used (\d+) registers", b).group(1))
+                smem = int(re.search(r"(\d+) bytes smem", b).group(1))
+                assert regs <= 42 and smem <= 24 * 1024, (regs, smem)
