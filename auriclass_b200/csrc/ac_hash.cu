@@ -203,14 +203,10 @@ __global__ void __launch_bounds__(K2_THREADS, AC_K2_MINB) k2_hash(const uint8_t 
         mbar_wait(s_bar, 0);
 
         // ---- once per sub-tile: reverse complement + validity / separator bitmaps (chunk = 32 bytes)
-#if defined(AC_K2_RC_UNROLL)
 #pragma unroll
-        for (uint32_t it = 0; it < (K2_TB / 32 + 31) / 32; it++) {
+        for (uint32_t it = 0; it < (K2_TB / 32 + 31) / 32; it++) {   // (unrolled: two chunks in flight per lane)
             const uint32_t c = lane + 32u * it;
             if (c >= K2_TB / 32) break;
-#else
-        for (uint32_t c = lane; c < K2_TB / 32; c += 32) {
-#endif
             uint32_t w[8];
             const uint4 a = reinterpret_cast<const uint4 *>(s_fwd)[2 * c], b4 = reinterpret_cast<const uint4 *>(s_fwd)[2 * c + 1];
             w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b4.x; w[5] = b4.y; w[6] = b4.z; w[7] = b4.w;
