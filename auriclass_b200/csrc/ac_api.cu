@@ -98,6 +98,7 @@ struct ac_ctx {
     double *d_dist, *d_p, *h_dist, *h_p;
     unsigned long long *d_common, *d_denom, *h_common, *h_denom;
     unsigned long long *d_qmeta, *h_qmeta;  // [3][max_q]: pointer, n, length
+    void *d_dist_parts;        // per-slice counts of the split dist kernels (DIST_SPLIT_MAX_PAIRS * 64 bytes)
     size_t dist_cap, q_cap;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<SketchBuf> sk_pool;
@@ -340,7 +341,7 @@ extern "C" void ac_destroy(ac_ctx *c) {
     free_select(c);
     cudaFree(c->d_Z[0]); cudaFree(c->d_Z[1]); cudaFree(c->d_st1); cudaFree(c->d_st2); cudaFree(c->d_jd); cudaFreeHost(c->h_jd);
     for (auto &s : c->slabs) cudaFree(s.ptr);
-    cudaFree(c->d_dist); cudaFree(c->d_p); cudaFree(c->d_common); cudaFree(c->d_denom); cudaFree(c->d_qmeta);
+    cudaFree(c->d_dist); cudaFree(c->d_p); cudaFree(c->d_common); cudaFree(c->d_denom); cudaFree(c->d_qmeta); cudaFree(c->d_dist_parts);
     cudaFreeHost(c->h_dist); cudaFreeHost(c->h_p); cudaFreeHost(c->h_common); cudaFreeHost(c->h_denom); cudaFreeHost(c->h_qmeta);
     for (auto ev : c->ev_pool) cudaEventDestroy(ev);
     for (int i = 0; i < 3; i++) for (auto &p : c->prof[i]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
@@ -1495,6 +1496,7 @@ static int ensure_dist(ac_ctx *c, size_t n_out, size_t n_q) {
         cudaFreeHost(c->h_dist); cudaFreeHost(c->h_p); cudaFreeHost(c->h_common); cudaFreeHost(c->h_denom);
         c->dist_cap = 0;
         const size_t cap = std::max<size_t>(n_out, 1024);
+        if (!c->d_dist_parts) CK(cudaMalloc(&c->d_dist_parts, (size_t)DIST_SPLIT_MAX_PAIRS * 64));
         CK(cudaMalloc(&c->d_dist, cap * 8)); CK(cudaMalloc(&c->d_p, cap * 8));
         CK(cudaMalloc(&c->d_common, cap * 8)); CK(cudaMalloc(&c->d_denom, cap * 8));
         CK(cudaHostAlloc(&c->h_dist, cap * 8, cudaHostAllocDefault)); CK(cudaHostAlloc(&c->h_p, cap * 8, cudaHostAllocDefault));
@@ -1539,7 +1541,7 @@ extern "C" int ac_dist_batch(ac_ctx *c, const ac_refs *refs, const ac_sketch *co
     LaunchCtx lc{c->s_comp, &c->launches};
     launch_dist(lc, refs->d_hash, refs->d_off, refs->d_len, refs->n_refs, (const unsigned long long *const *)c->d_qmeta,
                 c->d_qmeta + c->q_cap, c->d_qmeta + 2 * c->q_cap, n_q, refs->k, (unsigned long long)s_min, max_q, c->d_dist,
-                c->d_p, c->d_common, c->d_denom);
+                c->d_p, c->d_common, c->d_denom, c->d_dist_parts);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(c->h_dist, c->d_dist, n_out * 8, cudaMemcpyDeviceToHost, c->s_comp));
     CK(cudaMemcpyAsync(c->h_p, c->d_p, n_out * 8, cudaMemcpyDeviceToHost, c->s_comp));

@@ -186,7 +186,9 @@ void launch_dist(const LaunchCtx &lc, const unsigned long long *ref_hashes, cons
                  const unsigned long long *ref_len, int n_refs, const unsigned long long *const *q_hashes,
                  const unsigned long long *q_n, const unsigned long long *q_len, int n_q, int k,
                  unsigned long long sketch_size, unsigned long long max_q_n, double *d_dist, double *d_p,
-                 unsigned long long *d_common, unsigned long long *d_denom);
+                 unsigned long long *d_common, unsigned long long *d_denom, void *parts_scratch);
+// batches of up to this many pairs are split over several CTAs per pair; parts_scratch: DIST_SPLIT_MAX_PAIRS * 64 bytes
+constexpr int DIST_SPLIT_MAX_PAIRS = 256;
 
 // tile of pairs: sketches [i0, i0+ni) of set A against [j0, j0+nj) of set B, outputs [ni][nj] row-major
 void launch_dist_pairs(const LaunchCtx &lc, const unsigned long long *a_hashes, const unsigned long long *a_off,

@@ -89,34 +89,20 @@ __device__ double d_binomial_Q(u64 kk, double p, u64 n) {
     return 1.0 - sum;
 }
 
-__global__ void __launch_bounds__(D_THREADS) k5_dist(const u64 *__restrict__ ref_hashes, const u64 *__restrict__ ref_off,
-                                                     const u64 *__restrict__ ref_len, int n_refs,
-                                                     const u64 *const *__restrict__ q_hashes, const u64 *__restrict__ q_n,
-                                                     const u64 *__restrict__ q_len, int k, u64 S, double *__restrict__ o_dist,
-                                                     double *__restrict__ o_p, u64 *__restrict__ o_common,
-                                                     u64 *__restrict__ o_denom) {
-    extern __shared__ u64 s_samp[];  // ceil(max|Q| / 64) hashes (dynamic)
-    __shared__ uint32_t s_w[33];
-    __shared__ unsigned long long s_common_in;
-    const int ri = blockIdx.x % n_refs, qi = blockIdx.x / n_refs;
-    const u64 *R = ref_hashes + ref_off[ri];
-    const uint32_t nR = (uint32_t)(ref_off[ri + 1] - ref_off[ri]);
-    const u64 *Q = q_hashes[qi];
-    const uint32_t nQ = (uint32_t)q_n[qi];
+// R[i_begin .. i_end) against Q: every thread takes one hash per chunk of D_THREADS, finds its lower bound in Q (shared-memory
+// sample of every 64th hash, then one 512-byte block) and whether it is there; a block scan gives the common values before
+// it.  `carry` = common values of R[0 .. i_begin).  Returns (to all threads) the common values of the slice; per thread
+// `ranked` counts those of its common values whose union rank is <= S; *lb_first (thread 0) = lower bound of R[i_begin].
+__device__ __forceinline__ uint32_t dist_scan_slice(const u64 *__restrict__ R, uint32_t i_begin, uint32_t i_end,
+                                                    const u64 *__restrict__ Q, uint32_t nQ, const u64 *s_samp, uint32_t n_samp,
+                                                    uint32_t carry, u64 S, uint32_t *s_w, uint32_t &ranked, uint32_t *lb_first) {
     const uint32_t tid = threadIdx.x;
-    const uint32_t n_samp = (nQ + D_SAMPLE - 1) / D_SAMPLE;  // sample j = Q[j*64]
-    for (uint32_t j = tid; j < n_samp && j < D_MAX_SAMPLES; j += D_THREADS) s_samp[j] = Q[(size_t)j * D_SAMPLE];
-    if (tid == 0) s_common_in = 0;
-    __syncthreads();
-
-    uint32_t carry = 0;          // common values in earlier chunks
-    uint32_t my_common_in = 0;   // common values of this thread with union rank <= S
-    for (uint32_t c0 = 0; c0 < nR; c0 += D_THREADS) {
+    const uint32_t carry0 = carry;
+    for (uint32_t c0 = i_begin; c0 < i_end; c0 += D_THREADS) {
         const uint32_t i = c0 + tid;
         uint32_t lb = 0, isc = 0;
-        u64 x = 0;
-        if (i < nR) {
-            x = R[i];
+        if (i < i_end) {
+            const u64 x = R[i];
             // block search: largest sample index b with s_samp[b] < x  (block b covers Q[b*64 .. b*64+63])
             uint32_t lo = 0, hi = n_samp;  // first sample >= x in [lo, hi]
             while (lo < hi) {
@@ -132,39 +118,154 @@ __global__ void __launch_bounds__(D_THREADS) k5_dist(const u64 *__restrict__ ref
             }
             lb = a;
             isc = (lb < nQ && Q[lb] == x) ? 1u : 0u;
+            if (i == i_begin && lb_first) *lb_first = lb;
         }
         uint32_t tot;
         const uint32_t before = block_excl_sum<D_THREADS>(isc, s_w, tot) + carry;
         if (isc) {
             const u64 rank = (u64)i + 1 + lb - before;
-            if (rank <= S) my_common_in++;
+            if (rank <= S) ranked++;
         }
         carry += tot;
     }
-    if (my_common_in) atomicAdd(&s_common_in, (unsigned long long)my_common_in);
+    return carry - carry0;
+}
+
+// pair result from the counts: Mash distance, p-value (App. A.6); one thread
+__device__ void dist_write_pair(u64 common, u64 n_common_total, uint32_t nR, uint32_t nQ, int k, u64 S, u64 len_r, u64 len_q,
+                                double *o_dist, double *o_p, u64 *o_common, u64 *o_denom) {
+    const u64 uni = (u64)nR + nQ - n_common_total;
+    const u64 denom = uni < S ? uni : S;
+    double d;
+    if (common == denom) d = 0.0;
+    else if (common == 0) d = 1.0;
+    else {
+        const double jac = (double)common / (double)denom;
+        d = -log(2.0 * jac / (1.0 + jac)) / k;
+    }
+    double pv;
+    if (common == 0) pv = 1.0;
+    else {
+        const double space = scalbn(1.0, 2 * k);  // 4^k, exact
+        const double pX = 1.0 / (1.0 + space / (double)len_r);
+        const double pY = 1.0 / (1.0 + space / (double)len_q);
+        const double r = pX * pY / (pX + pY - pX * pY);
+        pv = d_binomial_Q(common - 1, r, denom);
+    }
+    *o_dist = d; *o_p = pv; *o_common = common; *o_denom = denom;
+}
+
+__device__ __forceinline__ uint32_t dist_load_sample(const u64 *__restrict__ Q, uint32_t nQ, u64 *s_samp) {
+    const uint32_t n_samp = (nQ + D_SAMPLE - 1) / D_SAMPLE;  // sample j = Q[j*64]
+    for (uint32_t j = threadIdx.x; j < n_samp && j < D_MAX_SAMPLES; j += D_THREADS) s_samp[j] = Q[(size_t)j * D_SAMPLE];
+    return n_samp;
+}
+
+// one CTA per (reference, query) pair: batches with enough pairs to fill the GPU
+__global__ void __launch_bounds__(D_THREADS) k5_dist(const u64 *__restrict__ ref_hashes, const u64 *__restrict__ ref_off,
+                                                     const u64 *__restrict__ ref_len, int n_refs,
+                                                     const u64 *const *__restrict__ q_hashes, const u64 *__restrict__ q_n,
+                                                     const u64 *__restrict__ q_len, int k, u64 S, double *__restrict__ o_dist,
+                                                     double *__restrict__ o_p, u64 *__restrict__ o_common,
+                                                     u64 *__restrict__ o_denom) {
+    extern __shared__ u64 s_samp[];  // ceil(max|Q| / 64) hashes (dynamic)
+    __shared__ uint32_t s_w[33];
+    __shared__ unsigned long long s_common_in;
+    const int ri = blockIdx.x % n_refs, qi = blockIdx.x / n_refs;
+    const u64 *R = ref_hashes + ref_off[ri];
+    const uint32_t nR = (uint32_t)(ref_off[ri + 1] - ref_off[ri]);
+    const u64 *Q = q_hashes[qi];
+    const uint32_t nQ = (uint32_t)q_n[qi];
+    const uint32_t n_samp = dist_load_sample(Q, nQ, s_samp);
+    if (threadIdx.x == 0) s_common_in = 0;
     __syncthreads();
-    if (tid == 0) {
-        const u64 uni = (u64)nR + nQ - carry;
-        const u64 denom = uni < S ? uni : S;
-        const u64 common = s_common_in;
-        double d;
-        if (common == denom) d = 0.0;
-        else if (common == 0) d = 1.0;
-        else {
-            const double jac = (double)common / (double)denom;
-            d = -log(2.0 * jac / (1.0 + jac)) / k;
-        }
-        double pv;
-        if (common == 0) pv = 1.0;
-        else {
-            const double space = scalbn(1.0, 2 * k);  // 4^k, exact
-            const double pX = 1.0 / (1.0 + space / (double)ref_len[ri]);
-            const double pY = 1.0 / (1.0 + space / (double)q_len[qi]);
-            const double r = pX * pY / (pX + pY - pX * pY);
-            pv = d_binomial_Q(common - 1, r, denom);
-        }
+    uint32_t ranked = 0;
+    const uint32_t total = dist_scan_slice(R, 0, nR, Q, nQ, s_samp, n_samp, 0, S, s_w, ranked, nullptr);
+    if (ranked) atomicAdd(&s_common_in, (unsigned long long)ranked);
+    __syncthreads();
+    if (threadIdx.x == 0) {
         const size_t o = (size_t)qi * n_refs + ri;
-        o_dist[o] = d; o_p[o] = pv; o_common[o] = common; o_denom[o] = denom;
+        dist_write_pair(s_common_in, total, nR, nQ, k, S, ref_len[ri], q_len[qi], o_dist + o, o_p + o, o_common + o, o_denom + o);
+    }
+}
+
+// ---- the 24 pairs of one isolate: D_SPLIT CTAs per pair.  Union ranks grow with the position in R, so the values whose rank is
+// <= S form a prefix of R: a first kernel counts every slice's common values (and the lower bound of its first hash), a
+// second one finds the slice the cap falls into from those numbers and walks only that slice again with the exact carry.
+constexpr int D_SPLIT = 8;
+struct DistPart { uint32_t common, lb_first; };
+
+__global__ void __launch_bounds__(D_THREADS) k5_dist_parts(const u64 *__restrict__ ref_hashes, const u64 *__restrict__ ref_off, int n_refs,
+                                                           const u64 *const *__restrict__ q_hashes, const u64 *__restrict__ q_n,
+                                                           DistPart *__restrict__ parts) {
+    extern __shared__ u64 s_samp[];
+    __shared__ uint32_t s_w[33];
+    __shared__ uint32_t s_lb;
+    const uint32_t pair = blockIdx.x / D_SPLIT, part = blockIdx.x % D_SPLIT;
+    const int ri = pair % n_refs, qi = pair / n_refs;
+    const u64 *R = ref_hashes + ref_off[ri];
+    const uint32_t nR = (uint32_t)(ref_off[ri + 1] - ref_off[ri]);
+    const u64 *Q = q_hashes[qi];
+    const uint32_t nQ = (uint32_t)q_n[qi];
+    const uint32_t per = (nR + D_SPLIT - 1) / D_SPLIT;
+    const uint32_t i0 = min(nR, part * per), i1 = min(nR, i0 + per);
+    const uint32_t n_samp = dist_load_sample(Q, nQ, s_samp);
+    if (threadIdx.x == 0) s_lb = 0;
+    __syncthreads();
+    uint32_t ranked = 0;
+    const uint32_t total = dist_scan_slice(R, i0, i1, Q, nQ, s_samp, n_samp, 0, ~0ULL, s_w, ranked, &s_lb);
+    __syncthreads();
+    if (threadIdx.x == 0) parts[blockIdx.x] = DistPart{total, s_lb};
+}
+
+__global__ void __launch_bounds__(D_THREADS) k5_dist_finish(const u64 *__restrict__ ref_hashes, const u64 *__restrict__ ref_off,
+                                                            const u64 *__restrict__ ref_len, int n_refs,
+                                                            const u64 *const *__restrict__ q_hashes, const u64 *__restrict__ q_n,
+                                                            const u64 *__restrict__ q_len, int k, u64 S,
+                                                            const DistPart *__restrict__ parts, double *__restrict__ o_dist,
+                                                            double *__restrict__ o_p, u64 *__restrict__ o_common,
+                                                            u64 *__restrict__ o_denom) {
+    extern __shared__ u64 s_samp[];
+    __shared__ uint32_t s_w[33];
+    __shared__ unsigned long long s_common_in;
+    const uint32_t pair = blockIdx.x;
+    const int ri = pair % n_refs, qi = pair / n_refs;
+    const u64 *R = ref_hashes + ref_off[ri];
+    const uint32_t nR = (uint32_t)(ref_off[ri + 1] - ref_off[ri]);
+    const u64 *Q = q_hashes[qi];
+    const uint32_t nQ = (uint32_t)q_n[qi];
+    const uint32_t per = (nR + D_SPLIT - 1) / D_SPLIT;
+    // common values before every slice; the last slice whose first hash still has a union rank <= S
+    uint32_t before[D_SPLIT + 1];
+    before[0] = 0;
+    int cap_part = -1;
+#pragma unroll
+    for (int p = 0; p < D_SPLIT; p++) {
+        const DistPart dp = parts[pair * D_SPLIT + p];
+        const uint32_t i0 = min(nR, (uint32_t)p * per);
+        if (i0 < nR && (u64)i0 + 1 + dp.lb_first - before[p] <= S) cap_part = p;   // rank of R[i0]
+        before[p + 1] = before[p] + dp.common;
+    }
+    uint32_t ranked = 0;
+    uint32_t common_before = 0;
+    if (threadIdx.x == 0) s_common_in = 0;
+    if (cap_part >= 0) {
+        const uint32_t n_samp = dist_load_sample(Q, nQ, s_samp);
+        __syncthreads();
+        uint32_t i0 = 0, i1 = 0;
+#pragma unroll
+        for (int p = 0; p < D_SPLIT; p++)
+            if (p == cap_part) { i0 = min(nR, (uint32_t)p * per); i1 = min(nR, i0 + per); common_before = before[p]; }
+        dist_scan_slice(R, i0, i1, Q, nQ, s_samp, n_samp, common_before, S, s_w, ranked, nullptr);
+    } else {
+        __syncthreads();
+    }
+    if (ranked) atomicAdd(&s_common_in, (unsigned long long)ranked);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const size_t o = (size_t)qi * n_refs + ri;
+        dist_write_pair((u64)common_before + s_common_in, before[D_SPLIT], nR, nQ, k, S, ref_len[ri], q_len[qi], o_dist + o, o_p + o,
+                        o_common + o, o_denom + o);
     }
 }
 
@@ -393,16 +494,29 @@ void launch_dist(const LaunchCtx &lc, const unsigned long long *ref_hashes, cons
                  const unsigned long long *ref_len, int n_refs, const unsigned long long *const *q_hashes,
                  const unsigned long long *q_n, const unsigned long long *q_len, int n_q, int k,
                  unsigned long long sketch_size, unsigned long long max_q_n, double *d_dist, double *d_p,
-                 unsigned long long *d_common, unsigned long long *d_denom) {
+                 unsigned long long *d_common, unsigned long long *d_denom, void *parts_scratch) {
     if (n_refs <= 0 || n_q <= 0) return;
     size_t smem = ((max_q_n + D_SAMPLE - 1) / D_SAMPLE) * sizeof(u64);
     if (smem > (size_t)D_MAX_SAMPLES * sizeof(u64)) smem = (size_t)D_MAX_SAMPLES * sizeof(u64);
     if (smem < 64) smem = 64;
     // beyond the 48 KB default the opt-in is needed -- per device (function attributes live in the context, not in the
     // process), so it is set whenever such a launch is made; a failure surfaces as the launch error the caller checks
+    const int n_pairs = n_refs * n_q;
+    if (parts_scratch && n_pairs <= DIST_SPLIT_MAX_PAIRS) {   // one isolate's pairs: D_SPLIT CTAs per pair, two launches
+        if (smem > 48u * 1024u) {
+            cudaFuncSetAttribute(k5_dist_parts, cudaFuncAttributeMaxDynamicSharedMemorySize, D_MAX_SAMPLES * (int)sizeof(u64));
+            cudaFuncSetAttribute(k5_dist_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, D_MAX_SAMPLES * (int)sizeof(u64));
+        }
+        DistPart *parts = static_cast<DistPart *>(parts_scratch);
+        k5_dist_parts<<<n_pairs * D_SPLIT, D_THREADS, smem, lc.stream>>>(ref_hashes, ref_off, n_refs, q_hashes, q_n, parts);
+        k5_dist_finish<<<n_pairs, D_THREADS, smem, lc.stream>>>(ref_hashes, ref_off, ref_len, n_refs, q_hashes, q_n, q_len, k, sketch_size,
+                                                              parts, d_dist, d_p, d_common, d_denom);
+        *lc.launches += 2;
+        return;
+    }
     if (smem > 48u * 1024u) cudaFuncSetAttribute(k5_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, D_MAX_SAMPLES * (int)sizeof(u64));
-    k5_dist<<<n_refs * n_q, D_THREADS, smem, lc.stream>>>(ref_hashes, ref_off, ref_len, n_refs, q_hashes, q_n, q_len, k,
-                                                       sketch_size, d_dist, d_p, d_common, d_denom);
+    k5_dist<<<n_pairs, D_THREADS, smem, lc.stream>>>(ref_hashes, ref_off, ref_len, n_refs, q_hashes, q_n, q_len, k,
+                                                  sketch_size, d_dist, d_p, d_common, d_denom);
     ++*lc.launches;
 }
 

@@ -112,6 +112,8 @@ def main():
         gen_s = time.perf_counter() - t0
         warm = [queries[i] for i in sorted(mine)[:3]]
         classify_batch(eng, warm, refs, k=K, s=S)                            # warm-up (fills the sketch-buffer pool)
+        if dist is not None:                                                 # ... and NCCL's point-to-point channels (first gather: ~1 s)
+            dist.gather_object({}, [None] * world if rank == 0 else None, dst=0)
         l0 = eng.launch_count()
         barrier()
         t0 = time.perf_counter()

@@ -12,7 +12,7 @@ python bench.py $prof > gpurun_out/bench_prof_${tag}.json 2> gpurun_out/bench_pr
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_${tag}.csv \
     python bench.py $prof > gpurun_out/ncu_list_${tag}.log 2>&1
 echo "ncu list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:'k1q_|k1_fa|k2_hash' -s 80 -c 8 \
+ncu --set full --clock-control none --import-source on -k regex:'k1q_|k1_fa|k2_hash' -s 40 -c 6 \
     -o gpurun_out/prof_${tag} -f python bench.py $prof > gpurun_out/ncu_full_${tag}.log 2>&1
 echo "ncu full rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:'bs_|k3t|k4_|rs_' -s 10 -c 16 \
