@@ -553,7 +553,8 @@ def main() -> None:
         alu_floor_s = n_kmers * 44.0 / pipe["lop3"] if pipe["lop3"] > 0 else 0.0
         floor_s = max(fma_floor_s, alu_floor_s)
         seg_mb = int(os.environ.get("AC_SEG_MB", "256"))
-        n_seg = max(1, -(-nbytes // (seg_mb << 20)))  # K2 launches per step = segments (ac_common.cuh SEG_BYTES)
+        n_seg = max(1, -(-nbytes // (seg_mb << 20)))  # segments per step (ac_common.cuh SEG_BYTES); K2 runs once per segment,
+        k2_launches = n_seg + (1 if min(nbytes, seg_mb << 20) >= (32 << 20) else 0)   # and twice over the first one (ac_api.cu run_segment)
         traffic = None
         tp = ROOT / "profiles" / "k2_traffic.json"
         if tp.exists():
@@ -599,8 +600,10 @@ def main() -> None:
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": k2_bytes / hash_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": k2_bytes / hash_s / 1e9 / hbm_peak, "traffic": traffic,
-                         "kernel": "k2_hash<27, FLAT>", "launches_per_step": int(n_seg), "avg_launch_ms": prof["hash_ms"] / n_seg,
-                         "algorithmic_bytes_per_launch": k2_bytes / n_seg, "peak_source": peak_src,
+                         "kernel": "k2_hash<27, FLAT>", "launches_per_step": int(k2_launches), "segments_per_step": int(n_seg),
+                         "avg_segment_ms": prof["hash_ms"] / n_seg, "algorithmic_bytes_per_segment": k2_bytes / n_seg,
+                         "traffic_note": "DRAM bytes of one steady-state launch over a whole segment (ncu --set full, profiles/k2_traffic.json), "
+                                         "scaled to this run's bytes per segment", "peak_source": peak_src,
                          "note": "K2 is integer-issue bound, not HBM bound: see roofline_int"},
             "roofline_int": {"bound": "int32-issue", "achieved": n_kmers * I_ALG / hash_s / 1e12, "peak": int_peak / 1e12,
                              "unit": "Tinstr/s", "frac": n_kmers * I_ALG / hash_s / int_peak,
