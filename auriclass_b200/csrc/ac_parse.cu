@@ -302,18 +302,25 @@ __device__ __forceinline__ uint32_t lines_of(const LineMasks &lm, uint32_t r, ui
 // Aggregates compose ((nA, cA) then (nB, cB) = (nA + nB, cA[q] + cB[q - nA])), so a warp folds a window of 32
 // predecessors with one scan, a 64-bit rotate per lane (the four 16-bit class counts rotate as one register) and four
 // warp reductions.  The status words are cleared per segment by the launcher (no epoch tag fits beside 4 x 15 bits).
+// The aggregate goes out as soon as the tile is counted; the walk itself comes LATE, after the emit side: the phase the
+// emit side needs is first read off the text (a line that starts with '@' and whose next-but-one line starts with '+' is
+// a header) and checked against the chained value afterwards -- a wrong or missing guess costs a second emit pass, never
+// a wrong stream.
 // Output side: the tile's sequence lines ("runs": maximal stretches of emitted bytes, newline included) are listed in
-// shared memory as (output offset, source offset); every thread then PRODUCES aligned 16-byte vectors of the stream --
-// locates the run of its first byte by binary search, gathers 16 unaligned source bytes from the staged text (and 16
-// more from the next run when the vector straddles a record boundary), sanitises 4 bytes at a time and stores the
-// vector.  No lane idles on header / quality bytes, nothing is staged twice, and there is no per-thread byte loop.
-// NT threads per CTA, tile = 64 NT bytes (thread t owns the 32-byte chunks t and NT + t).  Measured per C2 isolate:
-// 256 threads / 16 KiB at 6 CTAs per SM (40 registers) 1.30 ms, at 5 CTAs (44 registers) 1.40 ms, 128 threads / 8 KiB 1.55 ms.
+// shared memory as (output offset, source offset); every thread then PRODUCES 16-byte vectors of the stream --
+// locates the run of its first byte (proportional guess + short walk), gathers 16 unaligned source bytes from the
+// staged text (and 16 more from the next run when the vector straddles a record boundary), sanitises 4 bytes at a time
+// -- into a staging area at tile-local alignment; once the output offset is known the staged stream goes to Z as
+// aligned 16-byte vectors.  No lane idles on header / quality bytes and there is no per-thread byte loop.
+// NT threads per CTA, tile = 64 NT bytes (thread t owns the 32-byte chunks t and NT + t).  Measured per C2 isolate with the
+// look-back in FRONT of the emit side: 256 threads / 16 KiB at 6 CTAs per SM (40 registers) 1.29 ms, at 5 CTAs 1.40 ms,
+// 128 threads / 8 KiB 1.55 ms; 64-tile windows 1.43 ms; all eight warps walking 1.52 ms.  With the late look-back (this
+// kernel: 48 registers, 37.5 KB of shared memory, 5 CTAs per SM): 1.25 ms.
 #ifndef AC_K1_NT
 #define AC_K1_NT 256
 #endif
 #ifndef AC_K1_MINB
-#define AC_K1_MINB 6
+#define AC_K1_MINB 5
 #endif
 constexpr int FQ_NT = AC_K1_NT, FQ_MINB = AC_K1_MINB;
 constexpr int FQ_MAXRUNS = 1024;                      // runs listed per tile; beyond that (reads of < ~12 bytes) a byte-wise path
@@ -352,11 +359,13 @@ __device__ __forceinline__ void block_excl_sum2(uint32_t &a, uint32_t &b, uint32
 template <int NT>
 struct FqShared {
     __align__(128) uint8_t text[FQ_PAD + 64 * NT + FQ_PAD];   // staged tile at text + FQ_PAD (TMA destination)
+    __align__(16) uint8_t out[FQ_PAD + 64 * NT + FQ_PAD];     // the tile's base stream at tile-local alignment (out + FQ_PAD)
     uint16_t run_out[FQ_MAXRUNS + 2], run_src[FQ_MAXRUNS + 2];
+    uint16_t nlpos[16];                                       // positions of the tile's first newlines (phase from the text)
     uint32_t w[66];
     uint32_t acc[4];
-    uint32_t last_nl[16], last_em[16];   // per (row, warp): ballot of "last byte of the chunk is a newline / is emitted"
-    uint32_t phase_in, out_off, n_out, n_runs;
+    uint32_t last_nl[16], last_em[16];
+    uint32_t p_cur, p_true, o_true;
     __align__(8) uint64_t bar;
 };
 
@@ -369,6 +378,57 @@ __device__ __forceinline__ void gather16(const uint8_t *text0, int s, uint32_t o
     for (int i = 0; i < 5; i++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[i]) : "r"(al + 4u * i));
 #pragma unroll
     for (int i = 0; i < 4; i++) out[i] = __funnelshift_r(v[i], v[i + 1], sh);
+}
+
+// The look-back of one tile (one full warp): walks back over the predecessors' status words, 32 per round trip, until an
+// inclusive prefix is met; returns the phase at the tile's first byte and its output offset.  Virtual tile -1 carries the
+// parser state the previous segment left.
+__device__ __forceinline__ void fq_lookback(const u64 *__restrict__ status, uint32_t tile, uint32_t phase0, uint32_t lane,
+                                            uint32_t &P, uint32_t &O) {
+    P = 0; O = 0;
+    uint32_t S_nl = 0, Sc[4] = {0, 0, 0, 0};     // composition of the tiles behind the current window, up to tile - 1
+    for (long long top = (long long)tile - 1;; top -= 32) {
+        const long long idx = top - 31 + lane;    // ascending with the lane
+        u64 w = 0;
+        if (idx >= 0) { do { w = ld_status(&status[idx]); } while ((w >> 62) == 0); }
+        else if (idx == -1) w = ((u64)FQS_INC << 62) | ((u64)(phase0 & 3u) << 60) | (u64)Z_CARRY;   // virtual tile -1
+        const uint32_t flag = (uint32_t)(w >> 62);
+        const unsigned inc_mask = __ballot_sync(FULL, flag == FQS_INC);
+        const int F = inc_mask ? 31 - __clz(inc_mask) : -1;   // nearest inclusive prefix of this window
+        const bool use = (int)lane > F && flag == FQS_AGG;
+        const uint32_t my_nl = use ? (uint32_t)(w >> 60) & 3u : 0u;
+        uint32_t pre = my_nl;                                 // newlines of the used lanes before this one
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, pre, d); if ((int)lane >= d) pre += t; }
+        const uint32_t W_nl = __shfl_sync(FULL, pre, 31);
+        pre -= my_nl;
+        // class counts as 4 x 16 bits; rotating left by 16 * pre re-indexes them to the window's first used tile
+        u64 x = 0;
+        if (use) x = (w & 0x7FFFu) | (((w >> 15) & 0x7FFFu) << 16) | (((w >> 30) & 0x7FFFu) << 32) | (((w >> 45) & 0x7FFFu) << 48);
+        const uint32_t rot = 16u * (pre & 3u);
+        x = rot ? ((x << rot) | (x >> (64u - rot))) : x;
+        const uint32_t W0 = __reduce_add_sync(FULL, (uint32_t)x & 0xFFFFu), W1 = __reduce_add_sync(FULL, (uint32_t)(x >> 16) & 0xFFFFu);
+        const uint32_t W2 = __reduce_add_sync(FULL, (uint32_t)(x >> 32) & 0xFFFFu), W3 = __reduce_add_sync(FULL, (uint32_t)(x >> 48) & 0xFFFFu);
+        // window first, then what was folded before: c[q] = W[q] + S[q - W_nl]
+        const uint32_t Wc[4] = {W0, W1, W2, W3};
+        uint32_t N[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t from = (q - W_nl) & 3u;
+            N[q] = Wc[q] + (from == 0 ? Sc[0] : from == 1 ? Sc[1] : from == 2 ? Sc[2] : Sc[3]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) Sc[q] = N[q];
+        S_nl += W_nl;
+        if (inc_mask) {
+            const u64 wi = __shfl_sync(FULL, w, F);
+            const uint32_t Pi = (uint32_t)(wi >> 60) & 3u, Oi = (uint32_t)wi;
+            const uint32_t seq = (1u - Pi) & 3u;      // tile-local line index of the sequence lines right behind that tile
+            P = (Pi + S_nl) & 3u;
+            O = Oi + (seq == 0 ? Sc[0] : seq == 1 ? Sc[1] : seq == 2 ? Sc[2] : Sc[3]);
+            break;
+        }
+    }
 }
 
 template <int NT, int MINB>
@@ -460,205 +520,226 @@ __global__ void __launch_bounds__(NT, MINB) k1q_fused(SegDesc sd, uint32_t n_til
     }
     __syncthreads();
 
-    // ---- look-back (warp 0): phase at the tile's first byte, output offset
+    // ---- aggregate out at once; the look-back itself comes LATE (after the emit side), when the predecessors' aggregates have
+    // been out for a while.  The phase the emit side needs is first read off the text itself -- in 4-line FASTQ a line that
+    // starts with '@' and whose next-but-one line starts with '+' is a header -- and checked against the chained value
+    // afterwards (a wrong or missing guess costs a second emit pass, never a wrong stream).  With the look-back in front of
+    // the emit side 37 % of all stall samples sat at the barrier behind it: the walk waits for the YOUNGEST predecessors'
+    // aggregates, which are produced at the same time as this tile's (wider windows made it worse: 1.43 / 1.52 ms).
+    const uint32_t c0 = sh.acc[0], c1 = sh.acc[1], c2 = sh.acc[2], c3 = sh.acc[3];
     if (warp == 0) {
-        const uint32_t c0 = sh.acc[0], c1 = sh.acc[1], c2 = sh.acc[2], c3 = sh.acc[3];
-        uint32_t P, O;
-        if (tile == 0) { P = ps.fq_phase & 3u; O = Z_CARRY; }
+        if (tile > 0 && lane == 0) {
+            const u64 agg = ((u64)FQS_AGG << 62) | ((u64)(tile_nl & 3u) << 60) | ((u64)c3 << 45) | ((u64)c2 << 30) | ((u64)c1 << 15) | (u64)c0;
+            st_status(&status[tile], agg);
+        }
+        uint32_t p_spec = 0xFFu;
+        if (tile == 0) p_spec = ps.fq_phase & 3u;      // (exact)
         else {
-            if (lane == 0) {
-                const u64 agg = ((u64)FQS_AGG << 62) | ((u64)(tile_nl & 3u) << 60) | ((u64)c3 << 45) | ((u64)c2 << 30) | ((u64)c1 << 15) | (u64)c0;
-                st_status(&status[tile], agg);
+            // positions of the first newlines of the tile (warp 0 owns chunks 0..31: its first KiB)
+            const uint32_t cnt = __popc(nl[0]);
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, d); if ((int)lane >= d) inc += t; }
+            uint32_t kk = inc - cnt;
+            for (uint32_t x = nl[0]; x && kk < 16u; x &= x - 1, kk++) sh.nlpos[kk] = (uint16_t)(32u * lane + (uint32_t)(__ffs(x) - 1));
+            const uint32_t m = min(16u, __shfl_sync(FULL, inc, 31));
+            __syncwarp();
+            bool hit = false;
+            if (lane + 2 < m) {
+                const uint32_t h = sh.nlpos[lane] + 1u, q = sh.nlpos[lane + 2] + 1u;
+                hit = (long long)q < want && text0[h] == '@' && text0[q] == '+';
             }
-            uint32_t S_nl = 0, Sc[4] = {0, 0, 0, 0};     // composition of the tiles behind the current window, up to tile - 1
-            P = 0; O = 0;
-            for (long long top = (long long)tile - 1;; top -= 32) {
-                const long long idx = top - 31 + lane;    // ascending with the lane
-                u64 w = 0;
-                if (idx >= 0) { do { w = ld_status(&status[idx]); } while ((w >> 62) == 0); }
-                else if (idx == -1) w = ((u64)FQS_INC << 62) | ((u64)(ps.fq_phase & 3u) << 60) | (u64)Z_CARRY;   // virtual tile -1
-                const uint32_t flag = (uint32_t)(w >> 62);
-                const unsigned inc_mask = __ballot_sync(FULL, flag == FQS_INC);
-                const int F = inc_mask ? 31 - __clz(inc_mask) : -1;   // nearest inclusive prefix of this window
-                const bool use = (int)lane > F && flag == FQS_AGG;
-                const uint32_t my_nl = use ? (uint32_t)(w >> 60) & 3u : 0u;
-                uint32_t pre = my_nl;                                 // newlines of the used lanes before this one
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, pre, d); if ((int)lane >= d) pre += t; }
-                const uint32_t W_nl = __shfl_sync(FULL, pre, 31);
-                pre -= my_nl;
-                // class counts as 4 x 16 bits; rotating left by 16 * pre re-indexes them to the window's first used tile
-                u64 x = 0;
-                if (use) x = (w & 0x7FFFu) | (((w >> 15) & 0x7FFFu) << 16) | (((w >> 30) & 0x7FFFu) << 32) | (((w >> 45) & 0x7FFFu) << 48);
-                const uint32_t rot = 16u * (pre & 3u);
-                x = rot ? ((x << rot) | (x >> (64u - rot))) : x;
-                const uint32_t W0 = __reduce_add_sync(FULL, (uint32_t)x & 0xFFFFu), W1 = __reduce_add_sync(FULL, (uint32_t)(x >> 16) & 0xFFFFu);
-                const uint32_t W2 = __reduce_add_sync(FULL, (uint32_t)(x >> 32) & 0xFFFFu), W3 = __reduce_add_sync(FULL, (uint32_t)(x >> 48) & 0xFFFFu);
-                // window first, then what was folded before: c[q] = W[q] + S[q - W_nl]
-                const uint32_t Wc[4] = {W0, W1, W2, W3};
-                uint32_t N[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t from = (q - W_nl) & 3u;
-                    N[q] = Wc[q] + (from == 0 ? Sc[0] : from == 1 ? Sc[1] : from == 2 ? Sc[2] : Sc[3]);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; q++) Sc[q] = N[q];
-                S_nl += W_nl;
-                if (inc_mask) {
-                    const u64 wi = __shfl_sync(FULL, w, F);
-                    const uint32_t Pi = (uint32_t)(wi >> 60) & 3u, Oi = (uint32_t)wi;
-                    const uint32_t seq = (1u - Pi) & 3u;      // tile-local line index of the sequence lines right behind that tile
-                    P = (Pi + S_nl) & 3u;
-                    O = Oi + (seq == 0 ? Sc[0] : seq == 1 ? Sc[1] : seq == 2 ? Sc[2] : Sc[3]);
-                    break;
-                }
-            }
+            const unsigned hm = __ballot_sync(FULL, hit);
+            if (hm) p_spec = (0u - (uint32_t)__ffs(hm)) & 3u;     // the line behind newline k is a header: P + k + 1 = 0 (mod 4)
         }
-        const uint32_t seq = (1u - P) & 3u, qual = (3u - P) & 3u;
-        const uint32_t out_bytes = seq == 0 ? c0 : seq == 1 ? c1 : seq == 2 ? c2 : c3;
-        const uint32_t q_bytes = qual == 0 ? c0 : qual == 1 ? c1 : qual == 2 ? c2 : c3;
-        if (lane == 0) {
-            st_status(&status[tile], ((u64)FQS_INC << 62) | ((u64)((P + tile_nl) & 3u) << 60) | (u64)(O + out_bytes));
-            sh.phase_in = P; sh.out_off = O; sh.n_out = out_bytes;
-            if (out_bytes) atomicAdd(&jd->fq_seq_bytes, (u64)out_bytes);
-            if (q_bytes) atomicAdd(&jd->fq_qual_bytes, (u64)q_bytes);
-        }
+        if (lane == 0) sh.p_cur = p_spec;
     }
     __syncthreads();
-    const uint32_t P = sh.phase_in, O = sh.out_off, n_out = sh.n_out;
-
-    // ---- emitted bytes (sequence lines incl. their newline), format checks, run list
-    uint32_t emit[2], err = 0;
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-        const uint32_t ch = (uint32_t)NT * r + tid;
-        const uint32_t ph = (P + L0[r]) & 3u;                     // phase of the line holding the chunk's first byte
-        emit[r] = lines_of(lm[r], (1u - ph) & 3u, valid[r]);
-        if (valid[r]) {
-            // is the byte in front of the chunk's first valid byte a newline?
-            bool prev_nl;
-            const long long pos = tile_lo + 32ll * ch;
-            const int vlo = __ffs(valid[r]) - 1;
-            if (pos + vlo == seg_lo) prev_nl = ps.at_line_start != 0;                 // first byte of the segment
-            else if (ch == 0) prev_nl = sd.base[tile_lo - 1] == '\n';                 // last byte of the previous tile
-            else if (lane > 0) prev_nl = (sh.last_nl[FQ_WARPS * r + warp] >> (lane - 1)) & 1u;
-            else if (warp > 0) prev_nl = sh.last_nl[FQ_WARPS * r + warp - 1] >> 31;
-            else prev_nl = sh.last_nl[FQ_WARPS - 1] >> 31;                                       // row 1 starts behind row 0's last chunk
-            const uint32_t ls = ((nl[r] << 1) | (prev_nl ? (1u << vlo) : 0u)) & valid[r];
-            if (ls) {
-                const uint32_t hdr = lines_of(lm[r], (0u - ph) & 3u, valid[r]), plus = lines_of(lm[r], (2u - ph) & 3u, valid[r]);
-                for (uint32_t x = ls & (hdr | plus); x; x &= x - 1) {
-                    const int b = __ffs(x) - 1;
-                    const uint8_t c = text0[32u * ch + b];
-                    if ((hdr >> b) & 1u) { if (c != '@') err |= FERR_FQ_HEADER; }
-                    else if (c != '+') err |= FERR_FQ_PLUS;
-                }
-            }
-        }
-    }
-    if (err) atomicOr(&jd->format_error, err);
-    {
-        const uint32_t b0 = __ballot_sync(FULL, emit[0] >> 31), b1 = __ballot_sync(FULL, emit[1] >> 31);
-        if (lane == 0) { sh.last_em[warp] = b0; sh.last_em[FQ_WARPS + warp] = b1; }
-    }
-    __syncthreads();
-    uint32_t starts[2];
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-        uint32_t prev_em;      // is the byte in front of the chunk emitted?  (a tile always starts a new run)
-        if (lane > 0) prev_em = (sh.last_em[FQ_WARPS * r + warp] >> (lane - 1)) & 1u;
-        else if (warp > 0) prev_em = sh.last_em[FQ_WARPS * r + warp - 1] >> 31;
-        else prev_em = r ? sh.last_em[FQ_WARPS - 1] >> 31 : 0u;
-        starts[r] = emit[r] & ~((emit[r] << 1) | prev_em);
-    }
-    // exclusive prefixes over the chunks in stream order: emitted bytes, run starts (rows packed 16 | 16)
-    uint32_t eb = __popc(emit[0]) | (__popc(emit[1]) << 16), rs = __popc(starts[0]) | (__popc(starts[1]) << 16), tot_e, tot_r;
-    block_excl_sum2<FQ_THREADS>(eb, rs, sh.w, tot_e, tot_r);
-    const uint32_t E[2] = {eb & 0xFFFFu, (eb >> 16) + (tot_e & 0xFFFFu)};
-    const uint32_t R[2] = {rs & 0xFFFFu, (rs >> 16) + (tot_r & 0xFFFFu)};
-    const uint32_t n_runs = (tot_r & 0xFFFFu) + (tot_r >> 16);
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-        uint32_t k = R[r];
-        for (uint32_t x = starts[r]; x; x &= x - 1, k++) {
-            const int b = __ffs(x) - 1;
-            if (k < (uint32_t)FQ_MAXRUNS) {
-                sh.run_out[k] = (uint16_t)(E[r] + __popc(emit[r] & ((1u << b) - 1u)));
-                sh.run_src[k] = (uint16_t)(32u * ((uint32_t)NT * r + tid) + b);
-            }
-        }
-    }
-    if (tid == 0) { sh.n_runs = n_runs; }
-    __syncthreads();
-
-    // ---- produce the stream: Z[O .. O + n_out)
-    if (n_out) {
-        if (n_runs <= (uint32_t)FQ_MAXRUNS) {
-            const uint32_t v_first = O >> 4, v_end = (O + n_out + 15u) >> 4;
-            const float runs_per_byte = (float)n_runs / (float)n_out;
-            for (uint32_t v = v_first + tid; v < v_end; v += FQ_THREADS) {
-                const int o0 = (int)(v * 16u) - (int)O;              // tile-local output offset of the vector's first byte (may be < 0)
-                const uint32_t key = o0 < 0 ? 0u : (uint32_t)o0;
-                // last run with run_out <= key: reads of one length make runs of one length, so the proportional guess is
-                // right or one off; the walk behind it is exact for any input
-                uint32_t lo = min(n_runs - 1u, (uint32_t)((float)key * runs_per_byte));
-                while (sh.run_out[lo] > key) lo--;
-                while (lo + 1 < n_runs && sh.run_out[lo + 1] <= key) lo++;
-                const int avail = (lo + 1 < n_runs ? (int)sh.run_out[lo + 1] : 0x7fffffff) - o0;   // bytes of the vector served by run lo
-                uint32_t wv[4];
-                gather16(text0, (int)sh.run_src[lo] + (o0 - (int)sh.run_out[lo]), wv);
-                if (avail < 16) {
-                    const int avail2 = (lo + 2 < n_runs ? (int)sh.run_out[lo + 2] : 0x7fffffff) - o0;
-                    if (avail2 >= 16) {
-                        uint32_t w2[4];
-                        gather16(text0, (int)sh.run_src[lo + 1] - avail, w2);    // byte i >= avail is byte i - avail of run lo + 1
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const int na = avail - 4 * i;                        // bytes of word i that still belong to run lo
-                            const uint32_t m = na >= 4 ? 0xffffffffu : (na <= 0 ? 0u : ((1u << (8 * na)) - 1u));
-                            wv[i] = (wv[i] & m) | (w2[i] & ~m);
-                        }
-                    } else {
-                        // three or more runs inside 16 bytes (reads of a few bases): byte by byte
-                        uint32_t rr = lo;
-#pragma unroll
-                        for (int wi = 0; wi < 4; wi++) {
-                            uint32_t acc = 0;
-#pragma unroll
-                            for (int bi = 0; bi < 4; bi++) {
-                                const int o = o0 + 4 * wi + bi;
-                                while (rr + 1 < n_runs && (int)sh.run_out[rr + 1] <= o) rr++;
-                                const int sidx = (int)sh.run_src[rr] + (o - (int)sh.run_out[rr]);
-                                const uint32_t byte = (sidx >= -FQ_PAD && sidx < FQ_TILE + FQ_PAD) ? text0[sidx] : 0u;
-                                acc |= byte << (8 * bi);
-                            }
-                            wv[wi] = acc;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; i++) wv[i] = sanitise4_sep(wv[i]);
-                uint8_t *dst = Z + (size_t)v * 16u;
-                if (o0 >= 0 && (uint32_t)o0 + 16u <= n_out) {
-                    *reinterpret_cast<uint4 *>(dst) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const int o = o0 + i;
-                        if (o >= 0 && (uint32_t)o < n_out) dst[i] = (uint8_t)(wv[i >> 2] >> (8 * (i & 3)));
-                    }
-                }
-            }
-        } else {
-            // more runs than the list holds: every thread writes its own emitted bytes, one at a time
+    uint32_t P = sh.p_cur, O = 0, n_out = 0;
+    bool lb_done = false;
+    uint32_t emit[2] = {0, 0}, err = 0, E[2] = {0, 0}, n_runs = 0;
+    uint8_t *out0 = sh.out + FQ_PAD;
 #pragma unroll 1
-            for (int r = 0; r < 2; r++) {
-                uint32_t d = O + E[r];
-                for (uint32_t x = emit[r]; x; x &= x - 1, d++) {
-                    const int b = __ffs(x) - 1;
-                    const uint32_t c = text0[32u * ((uint32_t)NT * r + tid) + b];
-                    Z[d] = (uint8_t)(sanitise4_sep(c | 0x41414100u) & 0xFFu);
+    for (int attempt = 0; attempt < 3; attempt++) {
+        if (P == 0xFFu || attempt > 0) {
+            // no phase from the text (lines longer than the first KiB), or the guess was wrong: the chained value, now
+            if (!lb_done) {
+                if (warp == 0) {
+                    uint32_t Pt, Ot;
+                    if (tile == 0) { Pt = ps.fq_phase & 3u; Ot = Z_CARRY; } else fq_lookback(status, tile, ps.fq_phase, lane, Pt, Ot);
+                    if (lane == 0) { sh.p_true = Pt; sh.o_true = Ot; }
+                }
+                __syncthreads();
+                lb_done = true;
+            }
+            P = sh.p_true;
+        }
+        n_out = ((1u - P) & 3u) == 0 ? c0 : ((1u - P) & 3u) == 1 ? c1 : ((1u - P) & 3u) == 2 ? c2 : c3;
+
+        // ---- emitted bytes (sequence lines incl. their newline), format checks, run list
+        err = 0;
+    #pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const uint32_t ch = (uint32_t)NT * r + tid;
+            const uint32_t ph = (P + L0[r]) & 3u;                     // phase of the line holding the chunk's first byte
+            emit[r] = lines_of(lm[r], (1u - ph) & 3u, valid[r]);
+            if (valid[r]) {
+                // is the byte in front of the chunk's first valid byte a newline?
+                bool prev_nl;
+                const long long pos = tile_lo + 32ll * ch;
+                const int vlo = __ffs(valid[r]) - 1;
+                if (pos + vlo == seg_lo) prev_nl = ps.at_line_start != 0;                 // first byte of the segment
+                else if (ch == 0) prev_nl = sd.base[tile_lo - 1] == '\n';                 // last byte of the previous tile
+                else if (lane > 0) prev_nl = (sh.last_nl[FQ_WARPS * r + warp] >> (lane - 1)) & 1u;
+                else if (warp > 0) prev_nl = sh.last_nl[FQ_WARPS * r + warp - 1] >> 31;
+                else prev_nl = sh.last_nl[FQ_WARPS - 1] >> 31;                                       // row 1 starts behind row 0's last chunk
+                const uint32_t ls = ((nl[r] << 1) | (prev_nl ? (1u << vlo) : 0u)) & valid[r];
+                if (ls) {
+                    const uint32_t hdr = lines_of(lm[r], (0u - ph) & 3u, valid[r]), plus = lines_of(lm[r], (2u - ph) & 3u, valid[r]);
+                    for (uint32_t x = ls & (hdr | plus); x; x &= x - 1) {
+                        const int b = __ffs(x) - 1;
+                        const uint8_t c = text0[32u * ch + b];
+                        if ((hdr >> b) & 1u) { if (c != '@') err |= FERR_FQ_HEADER; }
+                        else if (c != '+') err |= FERR_FQ_PLUS;
+                    }
+                }
+            }
+        }
+        {
+            const uint32_t b0 = __ballot_sync(FULL, emit[0] >> 31), b1 = __ballot_sync(FULL, emit[1] >> 31);
+            if (lane == 0) { sh.last_em[warp] = b0; sh.last_em[FQ_WARPS + warp] = b1; }
+        }
+        __syncthreads();
+        uint32_t starts[2];
+    #pragma unroll
+        for (int r = 0; r < 2; r++) {
+            uint32_t prev_em;      // is the byte in front of the chunk emitted?  (a tile always starts a new run)
+            if (lane > 0) prev_em = (sh.last_em[FQ_WARPS * r + warp] >> (lane - 1)) & 1u;
+            else if (warp > 0) prev_em = sh.last_em[FQ_WARPS * r + warp - 1] >> 31;
+            else prev_em = r ? sh.last_em[FQ_WARPS - 1] >> 31 : 0u;
+            starts[r] = emit[r] & ~((emit[r] << 1) | prev_em);
+        }
+        // exclusive prefixes over the chunks in stream order: emitted bytes, run starts (rows packed 16 | 16)
+        uint32_t eb = __popc(emit[0]) | (__popc(emit[1]) << 16), rs = __popc(starts[0]) | (__popc(starts[1]) << 16), tot_e, tot_r;
+        block_excl_sum2<FQ_THREADS>(eb, rs, sh.w, tot_e, tot_r);
+        E[0] = eb & 0xFFFFu; E[1] = (eb >> 16) + (tot_e & 0xFFFFu);
+        const uint32_t R[2] = {rs & 0xFFFFu, (rs >> 16) + (tot_r & 0xFFFFu)};
+        n_runs = (tot_r & 0xFFFFu) + (tot_r >> 16);
+    #pragma unroll
+        for (int r = 0; r < 2; r++) {
+            uint32_t k = R[r];
+            for (uint32_t x = starts[r]; x; x &= x - 1, k++) {
+                const int b = __ffs(x) - 1;
+                if (k < (uint32_t)FQ_MAXRUNS) {
+                    sh.run_out[k] = (uint16_t)(E[r] + __popc(emit[r] & ((1u << b) - 1u)));
+                    sh.run_src[k] = (uint16_t)(32u * ((uint32_t)NT * r + tid) + b);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- produce the stream at tile-local alignment into the staging area (the output offset is not known yet)
+        if (n_out) {
+            if (n_runs <= (uint32_t)FQ_MAXRUNS) {
+                const uint32_t v_end = (n_out + 15u) >> 4;
+                const float runs_per_byte = (float)n_runs / (float)n_out;
+                for (uint32_t v = tid; v < v_end; v += FQ_THREADS) {
+                    const int o0 = (int)(v * 16u);                       // tile-local output offset of the vector's first byte
+                    const uint32_t key = o0 < 0 ? 0u : (uint32_t)o0;
+                    // last run with run_out <= key: reads of one length make runs of one length, so the proportional guess is
+                    // right or one off; the walk behind it is exact for any input
+                    uint32_t lo = min(n_runs - 1u, (uint32_t)((float)key * runs_per_byte));
+                    while (sh.run_out[lo] > key) lo--;
+                    while (lo + 1 < n_runs && sh.run_out[lo + 1] <= key) lo++;
+                    const int avail = (lo + 1 < n_runs ? (int)sh.run_out[lo + 1] : 0x7fffffff) - o0;   // bytes of the vector served by run lo
+                    uint32_t wv[4];
+                    gather16(text0, (int)sh.run_src[lo] + (o0 - (int)sh.run_out[lo]), wv);
+                    if (avail < 16) {
+                        const int avail2 = (lo + 2 < n_runs ? (int)sh.run_out[lo + 2] : 0x7fffffff) - o0;
+                        if (avail2 >= 16) {
+                            uint32_t w2[4];
+                            gather16(text0, (int)sh.run_src[lo + 1] - avail, w2);    // byte i >= avail is byte i - avail of run lo + 1
+    #pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                const int na = avail - 4 * i;                        // bytes of word i that still belong to run lo
+                                const uint32_t m = na >= 4 ? 0xffffffffu : (na <= 0 ? 0u : ((1u << (8 * na)) - 1u));
+                                wv[i] = (wv[i] & m) | (w2[i] & ~m);
+                            }
+                        } else {
+                            // three or more runs inside 16 bytes (reads of a few bases): byte by byte
+                            uint32_t rr = lo;
+    #pragma unroll
+                            for (int wi = 0; wi < 4; wi++) {
+                                uint32_t acc = 0;
+    #pragma unroll
+                                for (int bi = 0; bi < 4; bi++) {
+                                    const int o = o0 + 4 * wi + bi;
+                                    while (rr + 1 < n_runs && (int)sh.run_out[rr + 1] <= o) rr++;
+                                    const int sidx = (int)sh.run_src[rr] + (o - (int)sh.run_out[rr]);
+                                    const uint32_t byte = (sidx >= -FQ_PAD && sidx < FQ_TILE + FQ_PAD) ? text0[sidx] : 0u;
+                                    acc |= byte << (8 * bi);
+                                }
+                                wv[wi] = acc;
+                            }
+                        }
+                    }
+    #pragma unroll
+                    for (int i = 0; i < 4; i++) wv[i] = sanitise4_sep(wv[i]);
+                    reinterpret_cast<uint4 *>(out0)[v] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                }
+            } else {
+                // more runs than the list holds: every thread writes its own emitted bytes, one at a time
+    #pragma unroll 1
+                for (int r = 0; r < 2; r++) {
+                    uint32_t d = E[r];
+                    for (uint32_t x = emit[r]; x; x &= x - 1, d++) {
+                        const int b = __ffs(x) - 1;
+                        const uint32_t c = text0[32u * ((uint32_t)NT * r + tid) + b];
+                        out0[d] = (uint8_t)(sanitise4_sep(c | 0x41414100u) & 0xFFu);
+                    }
+                }
+            }
+        }
+
+
+        // ---- the look-back, late
+        __syncthreads();
+        if (!lb_done) {
+            if (warp == 0) {
+                uint32_t Pt, Ot;
+                if (tile == 0) { Pt = ps.fq_phase & 3u; Ot = Z_CARRY; } else fq_lookback(status, tile, ps.fq_phase, lane, Pt, Ot);
+                if (lane == 0) { sh.p_true = Pt; sh.o_true = Ot; }
+            }
+            __syncthreads();
+            lb_done = true;
+        }
+        if (sh.p_true == P) break;
+        __syncthreads();      // (wrong guess: once more with the chained phase; the run list and the staging area are rewritten)
+    }
+    O = sh.o_true;
+    if (err) atomicOr(&jd->format_error, err);
+    if (tid == 0) {
+        const uint32_t qual = (3u - P) & 3u;
+        const uint32_t q_bytes = qual == 0 ? c0 : qual == 1 ? c1 : qual == 2 ? c2 : c3;
+        st_status(&status[tile], ((u64)FQS_INC << 62) | ((u64)((P + tile_nl) & 3u) << 60) | (u64)(O + n_out));
+        if (n_out) atomicAdd(&jd->fq_seq_bytes, (u64)n_out);
+        if (q_bytes) atomicAdd(&jd->fq_qual_bytes, (u64)q_bytes);
+    }
+    // ---- staged stream -> Z[O .. O + n_out): aligned 16-byte vectors of Z, each from 16 unaligned staged bytes
+    if (n_out) {
+        const uint32_t v_first = O >> 4, v_end = (O + n_out + 15u) >> 4;
+        for (uint32_t v = v_first + tid; v < v_end; v += FQ_THREADS) {
+            const int o0 = (int)(v * 16u) - (int)O;
+            uint32_t wv[4];
+            gather16(out0, o0, wv);
+            uint8_t *dst = Z + (size_t)v * 16u;
+            if (o0 >= 0 && (uint32_t)o0 + 16u <= n_out) {
+                *reinterpret_cast<uint4 *>(dst) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const int o = o0 + i;
+                    if (o >= 0 && (uint32_t)o < n_out) dst[i] = (uint8_t)(wv[i >> 2] >> (8 * (i & 3)));
                 }
             }
         }
