@@ -1062,3 +1062,32 @@ def test_peer_exchange_through_the_sharder_world1(engine, reads):
             s_.close()
         engine._sharders.clear()
         dist.destroy_process_group()
+
+
+def test_fastq_phase_guess_from_the_text_is_verified(engine):
+    """k1q_fused reads the line phase of a tile off the text (a line that starts with '@' whose next-but-one line starts with
+    '+' is taken for a header) and checks it against the chained value after the emit side.  Records whose SEQUENCE line
+    starts with '@' and whose quality line starts with '+' make that rule misfire on half of the tiles; the stream must not
+    depend on it: same sketch for every shift of the tile grid (a prefix of k-mer-free records of varying size), and equal
+    to the oracle's on the same reads with the stray '@' spelled 'N' (both are just invalid bases to a strict 4-line parser)."""
+    rng = np.random.default_rng(99)
+    g = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 30_000)].tobytes()
+    recs_gpu, recs_ora = [], []
+    for i in range(6000):
+        L = int(rng.integers(40, 120))
+        o = int(rng.integers(0, len(g) - L))
+        seq = g[o:o + L]
+        hdr = b"@r%d" % i
+        recs_gpu.append(hdr + b"\n@" + seq + b"\n+\n+" + b"I" * L + b"\n")
+        recs_ora.append(hdr + b"\nN" + seq + b"\n+\n+" + b"I" * L + b"\n")
+    body_gpu, body_ora = b"".join(recs_gpu), b"".join(recs_ora)
+    assert len(body_gpu) > 40 * 16384
+    ref = oracle.sketch([body_ora], 21, 2000, 2)
+    assert len(ref.hashes) == 2000
+    for shift in (0, 1, 2, 3, 5, 64, 777, 16383):
+        prefix = b"@p\n" + b"N" * shift + b"\n+\n" + b"I" * shift + b"\n" if shift else b""
+        sk = engine.sketch_bytes([prefix + body_gpu], k=21, s=2000, m=2)
+        h, c = sk.hashes()
+        assert np.array_equal(h, ref.hashes) and np.array_equal(c, ref.counts), shift
+        assert sk.info["n_kmers"] == ref.n_kmers
+        sk.free()
