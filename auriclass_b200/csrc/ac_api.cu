@@ -1281,6 +1281,20 @@ extern "C" int ac_xchg_set_peer_local(ac_xchg *x, int r, ac_xchg *other) {
     return AC_OK;
 }
 
+// The owner merge runs in a 2 Mi-slot window of the count table (24 MB to clear instead of 96): an owner receives ~1/P of
+// every rank's entries <= tau_cut (C2 on 8 GPUs: ~50 k entries).  An inbox that does not fit raises the table's overflow
+// flag and ac_sketch_exchange_merge falls back to the sort-based merge.  AC_XCHG_MERGE_LOG2 resizes it (tests: 10).
+static CountTable xchg_merge_table(const ac_ctx *c, int min_copies) {
+    const char *e = getenv("AC_XCHG_MERGE_LOG2");
+    int log2_slots = e ? atoi(e) : 21;
+    if (log2_slots < 8) log2_slots = 8;
+    CountTable ctm = c->ct;
+    const int l2 = std::min(log2_slots, c->ct_log2);
+    ctm.mask = (uint32_t)(((size_t)1 << l2) - 1);
+    ctm.min_copies = (uint32_t)min_copies; ctm.bshift = 0;
+    return ctm;
+}
+
 extern "C" int ac_sketch_exchange_begin(ac_ctx *c, ac_job *j, ac_xchg *x, int k, int sketch_size, int min_copies, int failed) {
     if (!c || !x || x->ctx != c) return fail(AC_E_PARAM, "ac_sketch_exchange_begin: bad argument");
     if (x->phase != 0) return fail(AC_E_STATE, "an exchange is already in flight on this window");
@@ -1310,8 +1324,7 @@ extern "C" int ac_sketch_exchange_begin(ac_ctx *c, ac_job *j, ac_xchg *x, int k,
     }
     x->epoch++;
     LaunchCtx lc{c->s_comp, &c->launches};
-    CountTable ctm = c->ct;
-    ctm.min_copies = (uint32_t)min_copies; ctm.bshift = 0;
+    const CountTable ctm = xchg_merge_table(c, min_copies);
     launch_xchg_phase1(lc, x->peers, x->win, x->L, x->epoch, x->d_xl, c->d_jd, have_table, table_mode, x->local_rc ? 1ull : 0ull,
                        c->ct, c->sb, ctm);
     CK(cudaGetLastError());
@@ -1354,8 +1367,7 @@ extern "C" int ac_sketch_exchange_merge(ac_xchg *x) {
     } else {
         nq = x->h_jd2->n_qlist;
         if (nq) {
-            CountTable ctm = c->ct;
-            ctm.min_copies = (uint32_t)x->m; ctm.bshift = 0;
+            const CountTable ctm = xchg_merge_table(c, x->m);
             launch_table_collect(lc, ctm, c->sb, c->d_jd, (uint32_t)nq);
             launch_table_finish(lc, c->sb, c->d_jd, (uint32_t)nq, (uint32_t)nq, key_bits_for(x->h_jd2->max_hash), 0x7fffffff, 1);
             CK(cudaGetLastError());

@@ -50,21 +50,20 @@ __device__ bool wait_flag(const u64 *p, u64 epoch) {
 __device__ __forceinline__ XCtl *ctl_of(unsigned char *base) { return reinterpret_cast<XCtl *>(base); }
 
 // ---- phase 1 ---------------------------------------------------------------------------------------------------
-// tau_r (from the job state, or "everything" when this rank has no table) and the error word to every rank
-__global__ void kx_post_tau(XPeers peers, XLayout L, u64 epoch, const JobDev *__restrict__ jd, int have_table, u64 err) {
+// tau_r (from the job state, or "everything" when this rank has no table) and the error word go to every rank; then
+// tau_cut = min over ranks, range bounds b[r] = ceil(r * (tau_cut + 1) / P), cursors cleared.  (One launch: the post only
+// depends on this rank's own state.)
+__global__ void kx_wait_tau(XPeers peers, unsigned char *win, XLayout L, u64 epoch, XLocal *__restrict__ xl,
+                            const JobDev *__restrict__ jd, int have_table, u64 my_err) {
     const int r = threadIdx.x;
-    if (r >= (int)L.P) return;
-    XCtl *c = ctl_of(peers.base[r]);
-    c->tau_val[L.rank] = have_table ? jd->tau : ~0ULL;
-    c->tau_err[L.rank] = err;
-    __threadfence_system();
-    st_release_sys(&c->tau_flag[L.rank], epoch);
-}
-
-// tau_cut = min over ranks; range bounds b[r] = ceil(r * (tau_cut + 1) / P); cursors cleared
-__global__ void kx_wait_tau(unsigned char *win, XLayout L, u64 epoch, XLocal *__restrict__ xl) {
+    if (r < (int)L.P) {
+        XCtl *pc = ctl_of(peers.base[r]);
+        pc->tau_val[L.rank] = have_table ? jd->tau : ~0ULL;
+        pc->tau_err[L.rank] = my_err;
+        __threadfence_system();
+        st_release_sys(&pc->tau_flag[L.rank], epoch);
+    }
     XCtl *c = ctl_of(win);
-    const int r = threadIdx.x;
     u64 tau = ~0ULL;
     uint32_t err = 0;
     if (r < (int)L.P) {
@@ -164,9 +163,11 @@ __global__ void __launch_bounds__(256) kx_push(XPeers peers, XLayout L, u64 epoc
     }
 }
 
-__global__ void kx_wait_inbox(unsigned char *win, XLayout L, u64 epoch, XLocal *__restrict__ xl) {
+// (also leaves the job state the owner merge expects: empty qualified list, threshold "everything")
+__global__ void kx_wait_inbox(unsigned char *win, XLayout L, u64 epoch, XLocal *__restrict__ xl, JobDev *__restrict__ jd) {
     XCtl *c = ctl_of(win);
     const int r = threadIdx.x;
+    if (r == 0) { jd->tau = ~0ULL; jd->n_out = 0; jd->n_qlist = 0; jd->max_hash = 0; jd->overflow = 0; jd->n_qualified = 0; jd->n_sketch = 0; }
     uint32_t n = 0, err = 0;
     if (r < (int)L.P) {
         if (!wait_flag(&c->in_flag[r], epoch)) err |= XERR_TIMEOUT;
@@ -180,11 +181,6 @@ __global__ void kx_wait_inbox(unsigned char *win, XLayout L, u64 epoch, XLocal *
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) { tot += __shfl_xor_sync(FULL, tot, d); err |= __shfl_xor_sync(FULL, err, d); }
     if (r == 0) { xl->n_in_total = tot; if (err) atomicOr(&xl->err, err); }
-}
-
-// state the owner merge expects: empty qualified list, threshold "everything"
-__global__ void kx_reset_jd(JobDev *jd) {
-    jd->tau = ~0ULL; jd->n_out = 0; jd->n_qlist = 0; jd->max_hash = 0; jd->overflow = 0; jd->n_qualified = 0; jd->n_sketch = 0;
 }
 
 // owner merge: every (hash, count) of the P inboxes into the count table; a sum that crosses min_copies qualifies the key
@@ -333,9 +329,8 @@ XLayout xchg_layout(uint32_t rank, uint32_t P, uint32_t cap_in, uint32_t s_cap) 
 void launch_xchg_phase1(const LaunchCtx &lc, const XPeers &peers, unsigned char *win, const XLayout &L, u64 epoch, XLocal *xl,
                         JobDev *jd, int have_table, int table_mode, u64 err, const CountTable &ct_local, const SelectBufs &sb,
                         const CountTable &ct_merge) {
-    kx_post_tau<<<1, 32, 0, lc.stream>>>(peers, L, epoch, jd, have_table, err);
-    kx_wait_tau<<<1, 32, 0, lc.stream>>>(win, L, epoch, xl);
-    *lc.launches += 2;
+    kx_wait_tau<<<1, 32, 0, lc.stream>>>(peers, win, L, epoch, xl, jd, have_table, err);
+    ++*lc.launches;
     if (have_table) {
         if (table_mode) kx_scatter<true><<<XS_CTAS, XS_THREADS, 0, lc.stream>>>(ct_local, nullptr, nullptr, jd, L, xl, sb.keys_a, sb.vals_a);
         else kx_scatter<false><<<XS_CTAS, XS_THREADS, 0, lc.stream>>>(ct_local, sb.tab_hash, sb.tab_cnt, jd, L, xl, sb.keys_a, sb.vals_a);
@@ -346,10 +341,9 @@ void launch_xchg_phase1(const LaunchCtx &lc, const XPeers &peers, unsigned char 
     const size_t slots = (size_t)ct_merge.mask + 1;
     cudaMemsetAsync(ct_merge.key, 0xff, slots * 8, lc.stream);
     cudaMemsetAsync(ct_merge.cnt, 0, slots * 4, lc.stream);
-    kx_reset_jd<<<1, 1, 0, lc.stream>>>(jd);
-    kx_wait_inbox<<<1, 32, 0, lc.stream>>>(win, L, epoch, xl);
+    kx_wait_inbox<<<1, 32, 0, lc.stream>>>(win, L, epoch, xl, jd);
     kx_merge<<<148 * 4, 256, 0, lc.stream>>>(ct_merge, win, L, xl, jd);
-    *lc.launches += 4;
+    *lc.launches += 3;
 }
 
 void launch_xchg_compact_inbox(const LaunchCtx &lc, unsigned char *win, const XLayout &L, XLocal *xl, const SelectBufs &sb) {

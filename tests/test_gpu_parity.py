@@ -1091,3 +1091,22 @@ def test_fastq_phase_guess_from_the_text_is_verified(engine):
         assert np.array_equal(h, ref.hashes) and np.array_equal(c, ref.counts), shift
         assert sk.info["n_kmers"] == ref.n_kmers
         sk.free()
+
+
+def test_peer_exchange_owner_merge_falls_back_to_sorting(reads):
+    """the owner merge runs in a window of the count table; inboxes that do not fit it (here: a 1,024-slot window against
+    ~48,000 entries per owner) raise the overflow flag and the merge is redone by sorting -- same sketch"""
+    import os
+    os.environ["AC_XCHG_MERGE_LOG2"] = "10"
+    engines, wins = _peer_group(2)
+    try:
+        fq = reads[0] + reads[1]
+        sks = _exchange(engines, wins, [[x] for x in _split_fastq(fq, 2)], 27, 50000, 2)
+        ref = oracle.sketch([fq], 27, 50000, 2)
+        for sk in sks:
+            h, c = sk.hashes()
+            assert np.array_equal(h, ref.hashes) and np.array_equal(c, ref.counts)
+            assert sk.genome_size == ref.genome_size and sk.coverage == ref.coverage
+    finally:
+        del os.environ["AC_XCHG_MERGE_LOG2"]
+        _close_group(engines, wins)
