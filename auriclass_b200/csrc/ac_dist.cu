@@ -302,11 +302,17 @@ __device__ void d_finish_pair(u64 common, u64 denom, int k, u64 len_a, u64 len_b
 #ifndef AC_P_WARPS
 #define AC_P_WARPS 4
 #endif
-#ifndef AC_P_BLOCK
-#define AC_P_BLOCK 512
+#ifndef AC_P_PER
+#define AC_P_PER 17
 #endif
 constexpr int P_WARPS = AC_P_WARPS;      // pairs per CTA
-constexpr int P_BLOCK = AC_P_BLOCK;      // merged items per block and warp (2 x 8 P_BLOCK bytes of shared memory per warp)
+// Merged items per lane and block: ODD, so that the lanes' diagonals (P_PER apart in the B list during the split) and
+// their walk ranges (~P_PER / 2 apart in either list) fall into different shared-memory banks -- with 16 items per lane
+// every lane of the split's first steps hit the same bank (measured: 53 % of the kernel's shared-memory wavefronts).
+constexpr int P_PER = AC_P_PER;
+static_assert(P_PER % 2 == 1, "an even lane stride lines the lanes up on the same banks");
+constexpr int P_BLOCK = 32 * P_PER;      // merged items per block and warp (two buffers of 2 x 8 P_BLOCK bytes of shared memory per warp)
+__host__ __device__ constexpr uint32_t p_floor_pow2(uint32_t x) { uint32_t p = 1; while (2 * p <= x) p *= 2; return p; }
 
 struct PathPos { uint32_t i, j; };
 
@@ -347,17 +353,79 @@ __device__ __forceinline__ void merge_walk(const u64 *a, uint32_t na, const u64 
     distinct = dist; twins_in = tw; a_taken = i - p.i;
 }
 
+// 8-byte asynchronous copy global -> shared (LDGSTS): the staging loads of a block are all in flight at once and
+// need no registers, so the NEXT block's hashes travel while the warp walks the current one.
+constexpr int P_LIST = P_BLOCK + 8;      // slots per staged list: the walk reads (never uses) one slot past the end
+constexpr size_t P_SMEM = (size_t)P_WARPS * 2 * 2 * P_LIST * sizeof(u64);   // per warp: two buffers of (A block, B block)
+
+__device__ __forceinline__ uint32_t pairs_saddr(const u64 *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pairs_cp8(uint32_t dst, const u64 *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ u64 pairs_lds(uint32_t addr) {
+    u64 v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void pairs_stage(u64 *sa, u64 *sb, const u64 *A, uint32_t na, const u64 *B, uint32_t nb, uint32_t lane) {
+    const uint32_t da = pairs_saddr(sa + lane), db = pairs_saddr(sb + lane);
+    A += lane; B += lane;
+    if (na == (uint32_t)P_BLOCK && nb == (uint32_t)P_BLOCK) {      // full blocks: no bounds, offsets are immediates
+#pragma unroll
+        for (uint32_t q = 0; q < (uint32_t)P_PER; q++) pairs_cp8(da + 256 * q, A + 32 * q);
+#pragma unroll
+        for (uint32_t q = 0; q < (uint32_t)P_PER; q++) pairs_cp8(db + 256 * q, B + 32 * q);
+    } else {
+#pragma unroll 4
+        for (uint32_t q = 0; q < (uint32_t)P_PER; q++) if (lane + 32 * q < na) pairs_cp8(da + 256 * q, A + 32 * q);
+#pragma unroll 4
+        for (uint32_t q = 0; q < (uint32_t)P_PER; q++) if (lane + 32 * q < nb) pairs_cp8(db + 256 * q, B + 32 * q);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void pairs_stage_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// diagonal d of a FULL block (P_BLOCK staged values of either list, d <= P_BLOCK): the number of i in [0, d) with
+// a[i] <= b[d - 1 - i] (true up to the split, false after it), by a branch-free descent over fixed step sizes
+__device__ __forceinline__ uint32_t split_full(uint32_t sa, uint32_t sb, uint32_t d) {
+    uint32_t pos = 0;
+#pragma unroll
+    for (uint32_t step = p_floor_pow2(P_BLOCK); step >= 1; step >>= 1) {
+        const uint32_t t = pos + step;                  // candidate: are the first t values of a all before the split?
+        if (t <= d) {
+            const u64 av = pairs_lds(sa + 8 * (t - 1)), bv = pairs_lds(sb + 8 * (d - t));
+            if (av <= bv) pos = t;
+        }
+    }
+    return pos;
+}
+
+// the P_PER merged items of a full block that start at (i, j): twins among them.  No list can run out inside a full
+// block (i + j < P_BLOCK while the lane still has items), so there are no bounds and no sentinels: one compare, one
+// load of the list that moved.  last_a: the A value merged just before, or any value no B value before a[0] can equal.
+__device__ __forceinline__ uint32_t walk_full(uint32_t pa, uint32_t pb, u64 last_a) {
+    u64 av = pairs_lds(pa), bv = pairs_lds(pb);
+    uint32_t tw = 0;
+#pragma unroll
+    for (int t = 0; t < P_PER; t++) {
+        const bool ta = av <= bv;
+        if (ta) { last_a = av; pa += 8; av = pairs_lds(pa); }
+        else { tw += (bv == last_a) ? 1u : 0u; pb += 8; bv = pairs_lds(pb); }
+    }
+    return tw;
+}
+
 __global__ void __launch_bounds__(P_WARPS * 32) k5_pairs(const u64 *__restrict__ a_hashes, const u64 *__restrict__ a_off,
                                                          const u64 *__restrict__ a_len, uint32_t i0, uint32_t ni,
                                                          const u64 *__restrict__ b_hashes, const u64 *__restrict__ b_off,
                                                          const u64 *__restrict__ b_len, uint32_t j0, uint32_t nj, int k, u64 S,
                                                          double *__restrict__ o_dist, double *__restrict__ o_p,
                                                          u64 *__restrict__ o_common, u64 *__restrict__ o_denom) {
-    __shared__ u64 s_a_all[P_WARPS][P_BLOCK], s_b_all[P_WARPS][P_BLOCK];
+    extern __shared__ __align__(16) u64 s_pairs[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64 pair = (u64)blockIdx.x * P_WARPS + warp;
     if (pair >= (u64)ni * nj) return;
-    u64 *sa = s_a_all[warp], *sb = s_b_all[warp];
+    u64 *buf = s_pairs + (size_t)warp * 4 * P_LIST;        // [buffer][A | B][P_LIST]
     const uint32_t ia = i0 + (uint32_t)(pair / nj), jb = j0 + (uint32_t)(pair % nj);
     const u64 *A = a_hashes + a_off[ia];
     const uint32_t nA = (uint32_t)(a_off[ia + 1] - a_off[ia]);
@@ -368,6 +436,8 @@ __global__ void __launch_bounds__(P_WARPS * 32) k5_pairs(const u64 *__restrict__
     u64 rank = 0, common = 0;       // distinct values so far, twins of rank <= S so far
     u64 prev_a = 0;                 // last A value consumed (valid iff ci > 0)
     u64 uni = 0;                    // distinct values of the whole union, or any value >= S once the cap is known to decide
+    uint32_t cur = 0;
+    if (nA && nB) pairs_stage(buf, buf + P_LIST, A, min((uint32_t)P_BLOCK, nA), B, min((uint32_t)P_BLOCK, nB), lane);
     for (;;) {
         if (ci == nA || cj == nB) {
             // one list is exhausted: what is left of the other is all distinct, except a leading twin of prev_a
@@ -378,36 +448,57 @@ __global__ void __launch_bounds__(P_WARPS * 32) k5_pairs(const u64 *__restrict__
             break;
         }
         const uint32_t na = min((uint32_t)P_BLOCK, nA - ci), nb = min((uint32_t)P_BLOCK, nB - cj);
-        for (uint32_t t = lane; t < na; t += 32) sa[t] = A[ci + t];
-        for (uint32_t t = lane; t < nb; t += 32) sb[t] = B[cj + t];
+        const bool full = na == (uint32_t)P_BLOCK && nb == (uint32_t)P_BLOCK;
+        const u64 *sa = buf + (size_t)cur * 2 * P_LIST, *sb = sa + P_LIST;
+        pairs_stage_wait();
         __syncwarp();
         const uint32_t D = min((uint32_t)P_BLOCK, na + nb);   // the first D merged items only involve the staged values
         const uint32_t per = (D + 31) / 32;
         const uint32_t d0 = min(lane * per, D), d1 = min(d0 + per, D);
-        const PathPos p = merge_path_split(sa, na, sb, nb, d0);
-        uint32_t distinct, twins, a_taken;
-        merge_walk(sa, na, sb, nb, p, d1 - d0, prev_a, ci > 0, 0, ~0ULL, distinct, twins, a_taken);
-        uint32_t inc = distinct;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(FULL, inc, d);
-            if (lane >= (uint32_t)d) inc += t;
+        // every lane searches the END of its diagonal range; the start is the neighbour's end, and lane 31's end is
+        // the block's: the next block's position is known before the walk, so its hashes are requested now
+        PathPos pe;
+        if (full) { pe.i = split_full(pairs_saddr(sa), pairs_saddr(sb), d1); pe.j = d1 - pe.i; }
+        else pe = merge_path_split(sa, na, sb, nb, d1);
+        PathPos p;
+        p.i = __shfl_up_sync(FULL, pe.i, 1); p.j = __shfl_up_sync(FULL, pe.j, 1);
+        if (lane == 0) p = PathPos{0u, 0u};
+        const uint32_t a_used = __shfl_sync(FULL, pe.i, 31);
+        const uint32_t nci = ci + a_used, ncj = cj + (D - a_used);
+        if (nci < nA && ncj < nB) {
+            u64 *nbuf = buf + (size_t)(cur ^ 1) * 2 * P_LIST;
+            pairs_stage(nbuf, nbuf + P_LIST, A + nci, min((uint32_t)P_BLOCK, nA - nci), B + ncj, min((uint32_t)P_BLOCK, nB - ncj), lane);
         }
-        const uint32_t block_distinct = __shfl_sync(FULL, inc, 31);
+        uint32_t distinct, twins, a_taken;
+        if (full) {
+            const u64 last_a = p.i > 0 ? sa[p.i - 1] : (ci > 0 ? prev_a : sa[0]);
+            twins = walk_full(pairs_saddr(sa + p.i), pairs_saddr(sb + p.j), last_a);
+            distinct = (uint32_t)P_PER - twins;
+        } else {
+            merge_walk(sa, na, sb, nb, p, d1 - d0, prev_a, ci > 0, 0, ~0ULL, distinct, twins, a_taken);
+        }
+        const uint32_t block_twins = __reduce_add_sync(FULL, twins);
+        const uint32_t block_distinct = full ? (uint32_t)P_BLOCK - block_twins : __reduce_add_sync(FULL, distinct);
         if (rank + block_distinct > S) {
             // the cap falls inside this block: twins count only up to rank S, and the walk is over
+            uint32_t inc = distinct;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, inc, d);
+                if (lane >= (uint32_t)d) inc += t;
+            }
             uint32_t d2, tw2, a2;
             merge_walk(sa, na, sb, nb, p, d1 - d0, prev_a, ci > 0, rank + (inc - distinct), S, d2, tw2, a2);
             common += __reduce_add_sync(FULL, tw2);
             uni = rank + block_distinct;    // > S: the cap decides denom
             break;
         }
-        common += __reduce_add_sync(FULL, twins);
+        common += block_twins;
         rank += block_distinct;
-        const uint32_t a_used = __reduce_add_sync(FULL, a_taken);
         if (a_used) prev_a = sa[a_used - 1];
-        ci += a_used; cj += D - a_used;
-        __syncwarp();                       // the staging buffers are rewritten by the next block
+        ci = nci; cj = ncj;
+        cur ^= 1;
+        __syncwarp();                       // this block's buffer is the one the next iteration prefetches into
         if (rank == S) {
             // cap reached exactly at the block's end: only a twin of the last value could still count
             if (cj < nB && ci > 0 && B[cj] == prev_a) common += 1;
@@ -415,6 +506,7 @@ __global__ void __launch_bounds__(P_WARPS * 32) k5_pairs(const u64 *__restrict__
             break;
         }
     }
+    pairs_stage_wait();                     // a prefetch may still be in flight: it must land before the CTA's memory is reused
     if (lane == 0) {
         const u64 denom = uni < S ? uni : S;
         d_finish_pair(common, denom, k, a_len[ia], b_len[jb], o_dist + pair, o_p + pair);
@@ -527,7 +619,8 @@ void launch_dist_pairs(const LaunchCtx &lc, const unsigned long long *a_hashes, 
                        unsigned long long *d_denom) {
     const unsigned long long pairs = (unsigned long long)ni * nj;
     if (!pairs) return;
-    k5_pairs<<<div_up(pairs, P_WARPS), P_WARPS * 32, 0, lc.stream>>>(a_hashes, a_off, a_len, i0, ni, b_hashes, b_off, b_len, j0,
+    if (P_SMEM > 48u * 1024u) cudaFuncSetAttribute(k5_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM);
+    k5_pairs<<<div_up(pairs, P_WARPS), P_WARPS * 32, P_SMEM, lc.stream>>>(a_hashes, a_off, a_len, i0, ni, b_hashes, b_off, b_len, j0,
                                                                   nj, k, sketch_size, d_dist, d_p, d_common, d_denom);
     ++*lc.launches;
 }
