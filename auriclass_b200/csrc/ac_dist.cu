@@ -294,16 +294,27 @@ __device__ void d_finish_pair(u64 common, u64 denom, int k, u64 len_a, u64 len_b
 // ---- K5 for tiles of pairs (all-vs-all `mash dist`, BASELINE config 5): blocked merge path, one warp per pair.
 // The merged sequence of the two ascending lists (ties: the A element first, its B twin right behind it) is
 // consumed in blocks of P_BLOCK items.  Per block the warp stages the next P_BLOCK hashes of either list in
-// shared memory with coalesced loads, every lane finds its diagonal range by binary search (merge path) and walks
-// it from shared memory counting distinct values and twins; a warp scan turns the lane counts into ranks.
+// shared memory, every lane finds its diagonal range by binary search (merge path) and walks it from shared memory
+// counting twins (a B item equal to the A item merged just before it); distinct = items - twins.
 // Mash's capped merge (App. A.6) stops at the S-th distinct value and counts a twin of that value too, so:
 // common = twins whose rank (distinct values up to and including their A twin) is <= S, denom = min(S, distinct).
 // The walk ends as soon as the cap is reached or one list is exhausted -- the rest only adds to `distinct`.
+// Only the block the cap falls into needs per-lane ranks (a warp scan and a second, exact walk).
+//
+// What the kernel is bound by (ncu, profiles/r2_k5_pairs.md): shared-memory wavefronts -- the L1 data pipe is 80-93 %
+// busy, the issue slots 35 %.  Hence:
+//  * P_PER, the merged items per lane and block, is ODD: during the split's first steps the lanes probe the B list
+//    P_PER elements apart, and with 16 they all hit the same bank (53 % of the wavefronts, measured);
+//  * full blocks (both lists staged to P_BLOCK, i.e. all but the last one or two of a pair) take a branch-free split
+//    over fixed step sizes and a branch-free walk with ONE load per step and lane (the list that moved) and no
+//    bounds: inside a full block no list can run out while a lane still has items;
+//  * the next block's position is known after the split, before the walk: its hashes are requested then with
+//    asynchronous copies (LDGSTS, no registers) into the other buffer and land while the warp walks.
 #ifndef AC_P_WARPS
-#define AC_P_WARPS 4
+#define AC_P_WARPS 2      // measured on B200 (256 x 256 tiles, s = 50,000): 2 x 13: 8.43 ms, 4 x 13: 8.73, 4 x 17: 9.05, 6 x 9: 9.41
 #endif
 #ifndef AC_P_PER
-#define AC_P_PER 17
+#define AC_P_PER 13
 #endif
 constexpr int P_WARPS = AC_P_WARPS;      // pairs per CTA
 // Merged items per lane and block: ODD, so that the lanes' diagonals (P_PER apart in the B list during the split) and
@@ -408,9 +419,20 @@ __device__ __forceinline__ uint32_t walk_full(uint32_t pa, uint32_t pb, u64 last
     uint32_t tw = 0;
 #pragma unroll
     for (int t = 0; t < P_PER; t++) {
+#ifdef AC_P_TWO_LOADS
         const bool ta = av <= bv;
         if (ta) { last_a = av; pa += 8; av = pairs_lds(pa); }
         else { tw += (bv == last_a) ? 1u : 0u; pb += 8; bv = pairs_lds(pb); }
+#else
+        // ONE load per step for the whole warp (the list that moved, by lane): two predicated loads of half the
+        // lanes each cost more shared-memory wavefronts than one load of all of them
+        const bool ta = av <= bv;
+        tw += (!ta && bv == last_a) ? 1u : 0u;
+        last_a = ta ? av : last_a;
+        pa += ta ? 8u : 0u; pb += ta ? 0u : 8u;
+        const u64 nv = pairs_lds(ta ? pa : pb);
+        av = ta ? nv : av; bv = ta ? bv : nv;
+#endif
     }
     return tw;
 }

@@ -17,6 +17,7 @@ measurements beside bench.py's headline metric.  One JSON line per path (rank 0)
       checked against the oracle's sequential capped merge.
 """
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -91,6 +92,40 @@ def main():
         return float(t.item())
 
     eng = MashGPU(local)
+
+    class Stopwatch:
+        """wall time per call of an engine method, and -- with device=True -- the CUDA-event time of what the call put
+        on the compute stream (kernel + result copies), so that host overhead and kernel time can be told apart"""
+
+        def __init__(self, name, device=False):
+            self.name, self.device, self.wall_ms, self.dev_ms = name, device, [], []
+            self.orig = getattr(eng, name)
+            setattr(eng, name, self)
+
+        def __call__(self, *a, **kw):
+            if self.device:
+                eng.lib.ac_timer_start(eng.ctx)
+            t = time.perf_counter()
+            out = self.orig(*a, **kw)
+            self.wall_ms.append(1e3 * (time.perf_counter() - t))
+            if self.device:
+                ms = ctypes.c_float()
+                eng.lib.ac_timer_stop(eng.ctx, ctypes.byref(ms))
+                self.dev_ms.append(ms.value)
+            return out
+
+        def reset(self):
+            self.wall_ms, self.dev_ms = [], []
+
+        def stats(self):
+            st = {"calls": len(self.wall_ms), "wall_ms_total": float(np.sum(self.wall_ms)), "wall_ms_median": float(np.median(self.wall_ms)),
+                  "wall_ms_max": float(np.max(self.wall_ms))} if self.wall_ms else {"calls": 0}
+            if self.dev_ms:
+                st.update(device_ms_total=float(np.sum(self.dev_ms)), device_ms_median=float(np.median(self.dev_ms)))
+            return st
+
+        def restore(self):
+            setattr(eng, self.name, self.orig)
     if "c4" not in args.skip:
         g0 = synth.genome(20240001)
         refs_sk = []
@@ -110,8 +145,9 @@ def main():
         t0 = time.perf_counter()
         queries = [assembly(i) if i in mine else b"" for i in range(n)]     # a rank only materialises its own share
         gen_s = time.perf_counter() - t0
-        warm = [queries[i] for i in sorted(mine)[:3]]
-        classify_batch(eng, warm, refs, k=K, s=S)                            # warm-up (fills the sketch-buffer pool)
+        warm = [queries[i] for i in sorted(mine)[:64]]
+        classify_batch(eng, warm, refs, k=K, s=S)                            # warm-up (fills the pool of 64 sketch buffers a dist batch holds)
+        sw_sk, sw_di = Stopwatch("sketch_bytes"), Stopwatch("dist")
         if dist is not None:                                                 # ... and NCCL's point-to-point channels (first gather: ~1 s)
             dist.gather_object({}, [None] * world if rank == 0 else None, dst=0)
         l0 = eng.launch_count()
@@ -120,6 +156,7 @@ def main():
         rows = classify_batch(eng, queries, refs, k=K, s=S, rank=rank, world=world)
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
+        sw_sk.restore(); sw_di.restore()
         rec = None
         if rank == 0:
             from oracle import oracle
@@ -139,7 +176,7 @@ def main():
                    "Gbases_per_s": 12.4e6 * n / dt / 1e9, "gpu_launches_rank0": eng.launch_count() - l0,
                    "parity": {"checked_queries": checked, "rows_checked": 24 * len(checked), "equal": ok,
                               "against": "oracle.sketch_parallel + oracle.dist: common/denom bit for bit, distance and p-value 1e-12"},
-                   "generation_s_rank0": gen_s,
+                   "generation_s_rank0": gen_s, "rank0_calls": {"sketch_bytes": sw_sk.stats(), "dist": sw_di.stats()},
                    "includes": "H2D of the FASTA text from pageable host memory, K1/K2/count table, 24 dist rows per query, rows "
                                "gathered on rank 0 (gather_object); query q -> rank q mod P, references replicated"}
         if rec:
@@ -153,6 +190,7 @@ def main():
         gen_s = time.perf_counter() - t0
         list(all_pairs(eng, sset, min(64, len(sk)), tile=64))     # warm-up
         l0 = eng.launch_count()
+        sw_dp = Stopwatch("dist_pairs", device=True)
         barrier()
         t0 = time.perf_counter()
         pairs, common_sum, sample = 0, 0, []
@@ -163,6 +201,7 @@ def main():
                 sample.append(r)
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
+        sw_dp.restore()
         tot = np.array([pairs, common_sum], np.float64)
         if dist is not None:
             import torch
@@ -201,6 +240,8 @@ def main():
                   "parity": {"pairs_checked_per_rank": n_checked, "equal": ok,
                              "against": "oracle.dist (sequential capped merge): common/denom bit for bit, distance and p-value 1e-12"},
                   "gpu_launches_rank0": eng.launch_count() - l0, "generation_and_upload_s_rank0": gen_s,
+                  "rank0_calls": {"dist_pairs": sw_dp.stats()},
+                  "device_pairs_per_s_rank0": pairs / (sw_dp.stats()["device_ms_total"] / 1e3),
                   "includes": "upper-triangle tiles dealt round-robin over the ranks, four [tile, tile] result arrays copied back to the host per tile"})
         sset.free()
     eng.close()
