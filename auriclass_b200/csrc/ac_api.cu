@@ -1583,11 +1583,17 @@ extern "C" int ac_dist_pairs(ac_ctx *c, const ac_refs *a, int i0, int ni, const 
     launch_dist_pairs(lc, a->d_hash, a->d_off, a->d_len, (uint32_t)i0, (uint32_t)ni, b->d_hash, b->d_off, b->d_len, (uint32_t)j0,
                       (uint32_t)nj, a->k, (unsigned long long)std::min(a->s, b->s), c->d_dist, c->d_p, c->d_common, c->d_denom);
     CK(cudaGetLastError());
-    if (distance) CK(cudaMemcpyAsync(distance, c->d_dist, n_out * 8, cudaMemcpyDeviceToHost, c->s_comp));
-    if (pvalue) CK(cudaMemcpyAsync(pvalue, c->d_p, n_out * 8, cudaMemcpyDeviceToHost, c->s_comp));
-    if (common) CK(cudaMemcpyAsync(common, c->d_common, n_out * 8, cudaMemcpyDeviceToHost, c->s_comp));
-    if (denom) CK(cudaMemcpyAsync(denom, c->d_denom, n_out * 8, cudaMemcpyDeviceToHost, c->s_comp));
+    // results travel through the context's pinned buffers (a device-to-host copy into pageable memory runs at a few
+    // GB/s: 0.9 ms for the 2 MB of a 256 x 256 tile, a tenth of the kernel), then one memcpy each into the caller's arrays
+    if (distance) CK(cudaMemcpyAsync(c->h_dist, c->d_dist, n_out * 8, cudaMemcpyDeviceToHost, c->s_comp));
+    if (pvalue) CK(cudaMemcpyAsync(c->h_p, c->d_p, n_out * 8, cudaMemcpyDeviceToHost, c->s_comp));
+    if (common) CK(cudaMemcpyAsync(c->h_common, c->d_common, n_out * 8, cudaMemcpyDeviceToHost, c->s_comp));
+    if (denom) CK(cudaMemcpyAsync(c->h_denom, c->d_denom, n_out * 8, cudaMemcpyDeviceToHost, c->s_comp));
     CK(cudaStreamSynchronize(c->s_comp));
+    if (distance) memcpy(distance, c->h_dist, n_out * 8);
+    if (pvalue) memcpy(pvalue, c->h_p, n_out * 8);
+    if (common) memcpy(common, c->h_common, n_out * 8);
+    if (denom) memcpy(denom, c->h_denom, n_out * 8);
     return AC_OK;
 }
 

@@ -188,7 +188,7 @@ def main():
         sk = c5_sketches(args.sketches, S)
         sset = eng.load_sketch_set(sk, [12_400_000] * len(sk), K, S)
         gen_s = time.perf_counter() - t0
-        list(all_pairs(eng, sset, min(64, len(sk)), tile=64))     # warm-up
+        list(all_pairs(eng, sset, min(args.tile, len(sk)), tile=args.tile))     # warm-up: one full tile (sizes the result buffers)
         l0 = eng.launch_count()
         sw_dp = Stopwatch("dist_pairs", device=True)
         barrier()
