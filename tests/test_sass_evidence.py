@@ -106,3 +106,47 @@ def test_k1_fastq_parser_stages_its_tile_with_tma_and_fits_five_ctas():
                 regs = int(re.search(r"Used (\d+) registers", b).group(1))
                 smem = int(re.search(r"(\d+) bytes smem", b).group(1))
                 assert regs <= 51 and smem <= 40 * 1024, (regs, smem)
+
+
+def test_k5_pairs_prefetches_with_ldgsts_and_walks_without_branches():
+    """DESIGN.md section 5 (K5, all-vs-all): the next block is requested with asynchronous global -> shared copies
+    (LDGSTS) while the warp walks, and the walk of a full block is straight-line code -- P_PER unrolled steps of one
+    shared-memory load, two 64-bit compares and selects, no branch (the divergent walk of round 1 ran at 15 of 32 lanes)."""
+    obj = ROOT / "auriclass_b200" / "csrc" / "ac_dist.o"
+    if not obj.exists():
+        import __graft_entry__ as g
+        g.build()
+    out = subprocess.run(["cuobjdump", "-sass", str(obj)], capture_output=True, text=True, check=True).stdout
+    ins, on = [], False
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            on = "k5_pairs" in m.group(1)
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(.*?);", line)
+        if m and on:
+            ins.append(m.group(1).strip())
+    assert ins, "k5_pairs not found in ac_dist.o"
+    assert sum(1 for t in ins if "LDGSTS" in t) >= 2 * 13, "staging is not asynchronous"
+    assert any("LDGDEPBAR" in t or "DEPBAR" in t for t in ins), "no wait on the copy group"
+    # the longest straight block holds the unrolled walk (its first step or two are scheduled into the code that picks the
+    # "A value before"): >= 11 of the 13 steps x (load + 4 compare instructions + selects)
+    best, cur, loads, best_loads = 0, 0, 0, 0
+    for t in ins:
+        if re.search(r"\b(BRA|CALL|BSSY|BSYNC|EXIT|RET|WARPSYNC)\b", t):
+            if cur > best:
+                best, best_loads = cur, loads
+            cur = loads = 0
+        else:
+            cur += 1
+            loads += 1 if re.match(r"(@!?P\d\s+)?LDS\.64", t) else 0
+    if cur > best:
+        best, best_loads = cur, loads
+    assert best >= 11 * 13 and best_loads >= 11, (best, best_loads)
+    log = ROOT / "auriclass_b200" / "csrc" / "ac_dist.ptxas.log"
+    if log.exists():
+        for b in re.split(r"ptxas info\s+: Compiling entry function ", log.read_text()):
+            if "k5_pairs" in b[:200]:
+                m = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", b)
+                assert m and m.group(2) == "0" and m.group(3) == "0", b[:300]
+                assert int(re.search(r"Used (\d+) registers", b).group(1)) <= 64
