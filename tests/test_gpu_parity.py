@@ -572,6 +572,66 @@ def test_dist_pairs_tile_matches_oracle(engine, n, s, k, bits):
         sset.free()
 
 
+def _lists_from_pattern(pattern, start=1000, step=7):
+    """Two ascending hash lists whose merge reads as `pattern`: 'a' / 'b' = a value only in A / only in B, 't' = a value
+    in both (two merged items: the A element, its B twin right behind)."""
+    a, b, v = [], [], start
+    for ch in pattern:
+        if ch in "at":
+            a.append(v)
+        if ch in "bt":
+            b.append(v)
+        v += step
+    return np.array(a, np.uint64), np.array(b, np.uint64)
+
+
+def _n_items(pattern):
+    return sum(2 if ch == "t" else 1 for ch in pattern)
+
+
+@pytest.mark.parametrize("block", [416, 512, 544])
+def test_dist_pairs_at_block_boundaries(engine, block):
+    """k5_pairs consumes the merge in blocks (416 items: 13 per lane): caps that land exactly on a block's last item, twins
+    that straddle two blocks, lists that end with a block, blocks drawn from one list only -- every pattern for the
+    sketch sizes S that put the cap on, one before and one behind the boundary, against the oracle's sequential merge."""
+    rng = np.random.default_rng(block)
+    pats = {
+        "alternating": "ab" * (block + 40),
+        "all_twins": "t" * (block + 40),
+        "twin_straddles_block_1": "ab" * ((block - 2) // 2) + "a" + "t" + "ba" * 300,      # items block-1 / block are a twin pair
+        "twin_straddles_block_2": "ab" * (block - 1) + "a" + "t" + "ab" * 200,
+        "a_only_block": "a" * block + "ab" * 200,
+        "b_only_block": "b" * block + "ab" * 200,
+        "a_then_twins": "a" * (block - 1) + "t" * 300,
+        "ends_with_block": "ab" * (block // 2),
+        "ends_one_past": "ab" * (block // 2) + "a",
+        "twins_end_with_block": "t" * (block // 2),
+        "random_mix": "".join(rng.choice(list("abt"), size=3 * block, p=[0.35, 0.35, 0.3])),
+        "random_sparse_twins": "".join(rng.choice(list("abt"), size=3 * block, p=[0.49, 0.49, 0.02])),
+    }
+    for name, pat in pats.items():
+        assert _n_items(pat) >= block, name
+    lists = {name: _lists_from_pattern(pat) for name, pat in pats.items()}
+    # sketch sizes: distinct values up to the first / second block boundary of the simplest patterns, +- 1, and uncapped
+    for S in sorted({block // 2 - 1, block // 2, block // 2 + 1, block - 1, block, block + 1, 2 * block - 1, 2 * block, 2 * block + 1, 10 * block}):
+        sk, owner = [], []
+        for name, (a, b) in lists.items():
+            sk += [a, b]
+            owner += [name + ":A", name + ":B"]
+        lengths = [50_000 + 10 * i for i in range(len(sk))]
+        sset = engine.load_sketch_set(sk, lengths, 21, S)
+        try:
+            n = len(sk)
+            D, P, CM, DN = engine.dist_pairs(sset, 0, n, sset, 0, n)
+            for i in range(n):
+                for j in range(n):
+                    d, p, cm, dn = oracle.dist(sk[i], sk[j], S, 21, lengths[i], lengths[j])
+                    assert (int(CM[i, j]), int(DN[i, j])) == (cm, dn), (S, owner[i], owner[j], int(CM[i, j]), int(DN[i, j]), cm, dn)
+                    assert rel_close(D[i, j], d) and rel_close(P[i, j], p), (S, owner[i], owner[j])
+        finally:
+            sset.free()
+
+
 def test_dist_pairs_agrees_with_query_kernel(engine, ref_msh):
     """The tile kernel and the per-query kernel (ac_dist) give the same rows for the reference's own fixture."""
     refs = engine.load_references(D + "ref_sketch.msh")
