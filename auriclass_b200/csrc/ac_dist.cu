@@ -317,10 +317,7 @@ __device__ void d_finish_pair(u64 common, u64 denom, int k, u64 len_a, u64 len_b
 #define AC_P_PER 13
 #endif
 constexpr int P_WARPS = AC_P_WARPS;      // pairs per CTA
-// Merged items per lane and block: ODD, so that the lanes' diagonals (P_PER apart in the B list during the split) and
-// their walk ranges (~P_PER / 2 apart in either list) fall into different shared-memory banks -- with 16 items per lane
-// every lane of the split's first steps hit the same bank (measured: 53 % of the kernel's shared-memory wavefronts).
-constexpr int P_PER = AC_P_PER;
+constexpr int P_PER = AC_P_PER;          // merged items per lane and block (odd: see above)
 static_assert(P_PER % 2 == 1, "an even lane stride lines the lanes up on the same banks");
 constexpr int P_BLOCK = 32 * P_PER;      // merged items per block and warp (two buffers of 2 x 8 P_BLOCK bytes of shared memory per warp)
 __host__ __device__ constexpr uint32_t p_floor_pow2(uint32_t x) { uint32_t p = 1; while (2 * p <= x) p *= 2; return p; }
@@ -419,7 +416,7 @@ __device__ __forceinline__ uint32_t walk_full(uint32_t pa, uint32_t pb, u64 last
     uint32_t tw = 0;
 #pragma unroll
     for (int t = 0; t < P_PER; t++) {
-#ifdef AC_P_TWO_LOADS
+#ifdef AC_P_TWO_LOADS     // A/B switch of profiles/r2_k5_pairs.md: two predicated loads (9.3 ms per tile against 9.05)
         const bool ta = av <= bv;
         if (ta) { last_a = av; pa += 8; av = pairs_lds(pa); }
         else { tw += (bv == last_a) ? 1u : 0u; pb += 8; bv = pairs_lds(pb); }
